@@ -1,0 +1,431 @@
+// K1: FP64 DMMA GEMM for sm_100a.  See gemm.cuh.
+//
+// Design (B200): FP64 has no tcgen05/UMMA kind; the native FP64 tensor instruction on sm_100a is the warp-level
+// DMMA.8x8x4 (measured 37.2 TFLOP/s chip peak, 16 issue cycles per SM sub-partition, profiles/r01_fp64_peak_microbench.txt).
+// Accumulators live in registers; operand tiles are staged through shared memory by a 4-stage cp.async (LDGSTS)
+// pipeline in the orientation they have in HBM (k-contiguous or m/n-contiguous), with +4-double row padding that makes
+// every 8-byte fragment load conflict free.  The index permutations of the CTMRG contractions are folded into the
+// loader/epilogue address computation (Idx2), so no operand is ever transposed through HBM.
+#include "gemm.cuh"
+
+namespace ab200 {
+
+constexpr int BK = 16;
+constexpr int STAGES = 4;
+constexpr int PADK = BK + 4;   // row length (doubles) of a k-contiguous smem tile
+
+struct GemmKernelParams {
+    int M, N, K, batch, splitk, tiles_n, tiles_mn, kt_total;
+    GemmOperand A, B;
+    double* C;
+    Idx2 cm, cn, cb;
+    double alpha, beta;
+    double* ws;          // split-K partials [batch*splitk][M][N] (dense) when splitk > 1
+    int a_vec, b_vec;    // 16-byte loads allowed along the contiguous index
+};
+
+template <int BM, int BN, bool A_MC, bool B_KC>
+struct SmemLayout {
+    static constexpr int A_LD = A_MC ? (BM + 4) : PADK;
+    static constexpr int A_ROWS = A_MC ? BK : BM;
+    static constexpr int B_LD = B_KC ? PADK : (BN + 4);
+    static constexpr int B_ROWS = B_KC ? BN : BK;
+    static constexpr int A_ELEMS = A_ROWS * A_LD;
+    static constexpr int B_ELEMS = B_ROWS * B_LD;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+// Loads one operand tile (ROWS x COLS logical smem tile, COLS contiguous) with cp.async.
+//   CONTIG_IS_K : the contiguous (column) direction of the smem tile is the k index
+//   fix[]       : loop-invariant address part (non-k index) per chunk, -1 when out of range
+template <int ROWS, int COLS, int LD, int NT, bool CONTIG_IS_K>
+struct TileLoader {
+    static constexpr int CPR = COLS / 2;                       // 16-byte chunks per row
+    static constexpr int CHUNKS = ROWS * CPR;
+    static constexpr int PER_THREAD = (CHUNKS + NT - 1) / NT;
+};
+
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
+dgemm_dmma_kernel(const GemmKernelParams p) {
+    using L = SmemLayout<BM, BN, A_MC, B_KC>;
+    constexpr int NWARP_N = BN / WN;
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int wm0 = (warp / NWARP_N) * WM;
+    const int wn0 = (warp % NWARP_N) * WN;
+
+    const int bz = blockIdx.x / p.tiles_mn;
+    const int tile = blockIdx.x - bz * p.tiles_mn;
+    const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int b = bz / p.splitk, z = bz - b * p.splitk;
+    const int kt_begin = (int)(((long long)p.kt_total * z) / p.splitk);
+    const int kt_end = (int)(((long long)p.kt_total * (z + 1)) / p.splitk);
+    const int nkt = kt_end - kt_begin;
+
+    const double* __restrict__ Ab = p.A.ptr + p.A.batch.off(b);
+    const double* __restrict__ Bb = p.B.ptr + p.B.batch.off(b);
+
+    // ---- loader bookkeeping -------------------------------------------------------------------------------
+    // A tile: !A_MC: rows = m (BM), cols = k (BK) ; A_MC: rows = k (BK), cols = m (BM)
+    constexpr int A_ROWS = L::A_ROWS, A_COLS = A_MC ? BM : BK, A_CPR = A_COLS / 2;
+    constexpr int A_CH = (A_ROWS * A_CPR + NT - 1) / NT;
+    constexpr int B_ROWS = L::B_ROWS, B_COLS = B_KC ? BK : BN, B_CPR = B_COLS / 2;
+    constexpr int B_CH = (B_ROWS * B_CPR + NT - 1) / NT;
+
+    int64_t a_fix[A_CH];   // offset of the m index (loop invariant); for the 2 elements of a chunk when m is contiguous
+    int a_ok[A_CH];        // number of valid elements along m in this chunk (0..2) (A_MC) or 0/1 (!A_MC)
+    int64_t a_fix1[A_CH];  // offset of the second element (scalar path, m contiguous)
+#pragma unroll
+    for (int i = 0; i < A_CH; i++) {
+        int c = tid + i * NT;
+        int r = c / A_CPR, cp = c - r * A_CPR;
+        a_fix[i] = 0; a_fix1[i] = 0; a_ok[i] = 0;
+        if (c < A_ROWS * A_CPR) {
+            if (A_MC) {
+                int m = m0 + 2 * cp;
+                if (m < p.M) { a_fix[i] = p.A.row.off(m); a_ok[i] = 1; }
+                if (m + 1 < p.M) { a_fix1[i] = p.A.row.off(m + 1); a_ok[i] = 2; }
+            } else {
+                int m = m0 + r;
+                if (m < p.M) { a_fix[i] = p.A.row.off(m); a_ok[i] = 1; }
+            }
+        }
+    }
+    int64_t b_fix[B_CH], b_fix1[B_CH];
+    int b_ok[B_CH];
+#pragma unroll
+    for (int i = 0; i < B_CH; i++) {
+        int c = tid + i * NT;
+        int r = c / B_CPR, cp = c - r * B_CPR;
+        b_fix[i] = 0; b_fix1[i] = 0; b_ok[i] = 0;
+        if (c < B_ROWS * B_CPR) {
+            if (B_KC) {
+                int n = n0 + r;
+                if (n < p.N) { b_fix[i] = p.B.col.off(n); b_ok[i] = 1; }
+            } else {
+                int n = n0 + 2 * cp;
+                if (n < p.N) { b_fix[i] = p.B.col.off(n); b_ok[i] = 1; }
+                if (n + 1 < p.N) { b_fix1[i] = p.B.col.off(n + 1); b_ok[i] = 2; }
+            }
+        }
+    }
+
+    auto load_tile = [&](int stage, int kt) {
+        double* As = smem + (size_t)stage * L::STAGE_ELEMS;
+        double* Bs = As + L::A_ELEMS;
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < A_CH; i++) {
+            int c = tid + i * NT;
+            if (c >= A_ROWS * A_CPR) continue;
+            int r = c / A_CPR, cp = c - r * A_CPR;
+            double* dst = As + r * L::A_LD + 2 * cp;
+            if (A_MC) {
+                int k = k0 + r;
+                bool kok = k < p.K;
+                int64_t ko = kok ? p.A.col.off(k) : 0;
+                int nv = kok ? a_ok[i] : 0;
+                if (p.a_vec) {
+                    cp_async16(dst, Ab + a_fix[i] + ko, nv * 8);
+                } else {
+                    cp_async8(dst, Ab + a_fix[i] + ko, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Ab + a_fix1[i] + ko, nv >= 2 ? 8 : 0);
+                }
+            } else {
+                int k = k0 + 2 * cp;
+                int nv = a_ok[i] ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                if (p.a_vec) {
+                    int64_t ko = nv ? p.A.col.off(k) : 0;
+                    cp_async16(dst, Ab + a_fix[i] + ko, nv * 8);
+                } else {
+                    int64_t ko0 = nv >= 1 ? p.A.col.off(k) : 0;
+                    int64_t ko1 = nv >= 2 ? p.A.col.off(k + 1) : 0;
+                    cp_async8(dst, Ab + a_fix[i] + ko0, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Ab + a_fix[i] + ko1, nv >= 2 ? 8 : 0);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; i++) {
+            int c = tid + i * NT;
+            if (c >= B_ROWS * B_CPR) continue;
+            int r = c / B_CPR, cp = c - r * B_CPR;
+            double* dst = Bs + r * L::B_LD + 2 * cp;
+            if (B_KC) {
+                int k = k0 + 2 * cp;
+                int nv = b_ok[i] ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                if (p.b_vec) {
+                    int64_t ko = nv ? p.B.row.off(k) : 0;
+                    cp_async16(dst, Bb + b_fix[i] + ko, nv * 8);
+                } else {
+                    int64_t ko0 = nv >= 1 ? p.B.row.off(k) : 0;
+                    int64_t ko1 = nv >= 2 ? p.B.row.off(k + 1) : 0;
+                    cp_async8(dst, Bb + b_fix[i] + ko0, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Bb + b_fix[i] + ko1, nv >= 2 ? 8 : 0);
+                }
+            } else {
+                int k = k0 + r;
+                bool kok = k < p.K;
+                int64_t ko = kok ? p.B.row.off(k) : 0;
+                int nv = kok ? b_ok[i] : 0;
+                if (p.b_vec) {
+                    cp_async16(dst, Bb + b_fix[i] + ko, nv * 8);
+                } else {
+                    cp_async8(dst, Bb + b_fix[i] + ko, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Bb + b_fix1[i] + ko, nv >= 2 ? 8 : 0);
+                }
+            }
+        }
+    };
+
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int j = 0; j < NTL; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    // ---- pipeline prologue -----------------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nkt) load_tile(s, kt_begin + s);
+        cp_async_commit();
+    }
+
+    const int lr = lane >> 2, lc = lane & 3;
+    for (int it = 0; it < nkt; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = it + STAGES - 1;
+            if (nxt < nkt) load_tile(nxt % STAGES, kt_begin + nxt);
+            cp_async_commit();
+        }
+        const double* As = smem + (size_t)(it % STAGES) * L::STAGE_ELEMS;
+        const double* Bs = As + L::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double af[MT], bf[NTL];
+            const int k = kk * 4 + lc;
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+                int m = wm0 + i * 8 + lr;
+                af[i] = A_MC ? As[k * L::A_LD + m] : As[m * L::A_LD + k];
+            }
+#pragma unroll
+            for (int j = 0; j < NTL; j++) {
+                int n = wn0 + j * 8 + lr;
+                bf[j] = B_KC ? Bs[n * L::B_LD + k] : Bs[k * L::B_LD + n];
+            }
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    if (p.splitk > 1) {
+        double* W = p.ws + (size_t)bz * (size_t)p.M * (size_t)p.N;
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+            int m = m0 + wm0 + i * 8 + lr;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < NTL; j++) {
+                int n = n0 + wn0 + j * 8 + 2 * lc;
+                if (n < p.N) W[(size_t)m * p.N + n] = acc[i][j][0];
+                if (n + 1 < p.N) W[(size_t)m * p.N + n + 1] = acc[i][j][1];
+            }
+        }
+        return;
+    }
+    double* Cb = p.C + p.cb.off(b);
+    int64_t noff[NTL][2];
+#pragma unroll
+    for (int j = 0; j < NTL; j++) {
+        int n = n0 + wn0 + j * 8 + 2 * lc;
+        noff[j][0] = n < p.N ? p.cn.off(n) : -1;
+        noff[j][1] = n + 1 < p.N ? p.cn.off(n + 1) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+        int m = m0 + wm0 + i * 8 + lr;
+        if (m >= p.M) continue;
+        int64_t mo = p.cm.off(m);
+#pragma unroll
+        for (int j = 0; j < NTL; j++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (noff[j][e] < 0) continue;
+                double* dst = Cb + mo + noff[j][e];
+                double v = p.alpha * acc[i][j][e];
+                if (p.beta != 0.0) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
+
+// split-K reduction + general store:  C = alpha * sum_z ws[b][z] + beta * C
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int M, int N, int batch, int splitk, double* C,
+                                     Idx2 cm, Idx2 cn, Idx2 cb, double alpha, double beta) {
+    size_t total = (size_t)M * N * batch;
+    size_t mn = (size_t)M * N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int b = (int)(idx / mn);
+        size_t r = idx - (size_t)b * mn;
+        int m = (int)(r / N), n = (int)(r - (size_t)m * N);
+        const double* w = ws + (size_t)b * splitk * mn + r;
+        double s = 0.0;
+        for (int z = 0; z < splitk; z++) s += w[(size_t)z * mn];
+        double* dst = C + cb.off(b) + cm.off(m) + cn.off(n);
+        double v = alpha * s;
+        if (beta != 0.0) v += beta * (*dst);
+        *dst = v;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+    int tile;        // 1: 128x128, 2: 128x88, 3: 64x64
+    int bm, bn;
+    int splitk;
+    bool a_mc, b_kc;
+    int a_vec, b_vec;
+};
+
+inline bool even64(int64_t v) { return (v & 1) == 0; }
+
+// vectorisable along a contiguous two-level index: unit inner stride, pairs never straddle the div boundary
+inline bool contig_ok(const Idx2& x) { return x.s_lo == 1 && (x.div == 0 || ((x.div & 1) == 0 && even64(x.s_hi))); }
+inline bool strides_even(const Idx2& x) { return x.div == 0 ? even64(x.s_lo) : (even64(x.s_lo) && even64(x.s_hi)); }
+
+Plan make_plan(const GemmDesc& d) {
+    Plan pl;
+    // orientation: prefer the index with unit stride as the smem-contiguous one
+    bool a_k_unit = d.A.col.s_lo == 1, a_m_unit = d.A.row.s_lo == 1;
+    pl.a_mc = (!a_k_unit && a_m_unit) || (a_k_unit && a_m_unit && d.K == 1);
+    bool b_n_unit = d.B.col.s_lo == 1, b_k_unit = d.B.row.s_lo == 1;
+    pl.b_kc = (!b_n_unit && b_k_unit);
+    const bool a16 = (((uintptr_t)d.A.ptr) & 15) == 0, b16 = (((uintptr_t)d.B.ptr) & 15) == 0;
+    if (pl.a_mc) pl.a_vec = a16 && contig_ok(d.A.row) && strides_even(d.A.col) && strides_even(d.A.batch);
+    else         pl.a_vec = a16 && contig_ok(d.A.col) && strides_even(d.A.row) && strides_even(d.A.batch);
+    if (pl.b_kc) pl.b_vec = b16 && contig_ok(d.B.row) && strides_even(d.B.col) && strides_even(d.B.batch);
+    else         pl.b_vec = b16 && contig_ok(d.B.col) && strides_even(d.B.row) && strides_even(d.B.batch);
+
+    const int sms = device_sm_count();
+    auto waves_cost = [&](int bm, int bn, int splitk) {
+        long long tiles = (long long)((d.M + bm - 1) / bm) * ((d.N + bn - 1) / bn) * d.batch * splitk;
+        long long waves = (tiles + sms - 1) / sms;
+        // time ~ waves * tile_area * K/splitk  (+ fixed per-CTA overhead of ~6 k-tiles)
+        double kt = (double)((d.K + BK - 1) / BK) / splitk + 6.0;
+        double t = (double)waves * bm * bn * kt;
+        if (splitk > 1) t += 3.0 * (double)d.M * d.N * d.batch * splitk / sms * 2.0;   // partial write + reduce traffic
+        return t;
+    };
+    int tiles_opt[3][2] = {{128, 128}, {128, 88}, {64, 64}};
+    double best = 1e300;
+    pl.tile = 1; pl.bm = 128; pl.bn = 128; pl.splitk = 1;
+    const int kt_total = (d.K + BK - 1) / BK;
+    for (int t = 0; t < 3; t++) {
+        if (d.force_tile && d.force_tile != t + 1) continue;
+        int bm = tiles_opt[t][0], bn = tiles_opt[t][1];
+        for (int s = 1; s <= 64; s++) {
+            if (d.force_splitk && s != d.force_splitk) continue;
+            if (s > 1 && kt_total / s < 8) break;
+            double c = waves_cost(bm, bn, s);
+            if (t == 2) c *= 1.25;   // 64x64 tiles run at lower efficiency per flop
+            if (c < best) { best = c; pl.tile = t + 1; pl.bm = bm; pl.bn = bn; pl.splitk = s; }
+        }
+    }
+    if (d.force_splitk) pl.splitk = d.force_splitk;
+    return pl;
+}
+
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC>
+int launch_cfg(const GemmKernelParams& kp, cudaStream_t stream) {
+    using L = SmemLayout<BM, BN, A_MC, B_KC>;
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_KC>;
+    static bool configured = false;
+    if (!configured) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        configured = true;
+    }
+    GemmKernelParams k2 = kp;
+    int tiles_m = (kp.M + BM - 1) / BM;
+    k2.tiles_mn = tiles_m * kp.tiles_n;
+    long long nblk = (long long)k2.tiles_mn * kp.batch * kp.splitk;
+    if (nblk > 2147483647LL) { set_error("gemm: grid too large (%lld CTAs)", nblk); return ERR_INVALID; }
+    kern<<<(unsigned)nblk, NT, L::BYTES, stream>>>(k2);
+    AB_LAUNCHED();
+    return OK;
+}
+
+template <int BM, int BN, int WM, int WN>
+int launch_orient(const GemmKernelParams& kp, bool a_mc, bool b_kc, cudaStream_t stream) {
+    if (!a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, false, false>(kp, stream);
+    if (a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, true, false>(kp, stream);
+    if (!a_mc && b_kc) return launch_cfg<BM, BN, WM, WN, false, true>(kp, stream);
+    return launch_cfg<BM, BN, WM, WN, true, true>(kp, stream);
+}
+
+}  // namespace
+
+size_t gemm_workspace_bytes(const GemmDesc& d) {
+    if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return 0;
+    Plan pl = make_plan(d);
+    if (pl.splitk <= 1) return 0;
+    return ws_round((size_t)d.M * d.N * d.batch * pl.splitk * sizeof(double));
+}
+
+int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return OK;
+    AB_REQUIRE(d.K >= 0, "gemm: negative K");
+    Plan pl = make_plan(d);
+    GemmKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.M = d.M; kp.N = d.N; kp.K = d.K; kp.batch = d.batch; kp.splitk = pl.splitk;
+    kp.tiles_n = (d.N + pl.bn - 1) / pl.bn;
+    kp.kt_total = (d.K + BK - 1) / BK;
+    kp.A = d.A; kp.B = d.B; kp.C = d.C; kp.cm = d.cm; kp.cn = d.cn; kp.cb = d.cb;
+    kp.alpha = d.alpha; kp.beta = d.beta;
+    kp.a_vec = pl.a_vec; kp.b_vec = pl.b_vec;
+    kp.ws = nullptr;
+    if (pl.splitk > 1) {
+        size_t need = (size_t)d.M * d.N * d.batch * pl.splitk * sizeof(double);
+        if (ws == nullptr || ws_bytes < need) {
+            set_error("gemm: split-K workspace too small (%zu needed, %zu given)", need, ws_bytes);
+            return ERR_WORKSPACE;
+        }
+        kp.ws = (double*)ws;
+    }
+    int st;
+    if (pl.tile == 1) st = launch_orient<128, 128, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
+    else if (pl.tile == 2) st = launch_orient<128, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
+    else st = launch_orient<64, 64, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
+    if (st) return st;
+    if (pl.splitk > 1) {
+        size_t total = (size_t)d.M * d.N * d.batch;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(kp.ws, d.M, d.N, d.batch, pl.splitk, d.C, d.cm, d.cn, d.cb,
+                                                        d.alpha, d.beta);
+        AB_LAUNCHED();
+    }
+    return OK;
+}
+
+}  // namespace ab200

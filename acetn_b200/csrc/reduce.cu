@@ -1,0 +1,221 @@
+// K3: HBM-bound helpers (max-abs, Frobenius normalisation, gathers, column scaling).  All are single-pass,
+// coalesced, grid sized as a multiple of the SM count; reductions are deterministic (fixed-order two-stage) except
+// max-abs, which is order independent.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "kernels.cuh"
+
+namespace ab200 {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launch_counter{0};
+void note_launch(int n) { g_launch_counter.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launch_counter.load(); }
+void reset_launch_count() { g_launch_counter.store(0); }
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+constexpr int RED_BLOCKS = 148 * 4;
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < RED_THREADS / 32; i++) s += red[i];
+    __syncthreads();
+    return s;
+}
+
+__global__ void absmax_kernel(const double* __restrict__ x, size_t n, double* dst) {
+    double m = 0.0;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2, step = (size_t)gridDim.x * blockDim.x * 2;
+    if ((((uintptr_t)x) & 15) == 0) {
+        for (; i + 1 < n; i += step) {
+            double2 v = *reinterpret_cast<const double2*>(x + i);
+            m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+        }
+        if (i < n) m = fmax(m, fabs(x[i]));
+    } else {
+        for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) m = fmax(m, fabs(x[j]));
+    }
+    m = warp_max(m);
+    __shared__ double red[RED_THREADS / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int k = 0; k < RED_THREADS / 32; k++) r = fmax(r, red[k]);
+        atomic_max_nonneg(dst, r);
+    }
+}
+
+__global__ void scale_inv_kernel(double* __restrict__ x, size_t n, const double* __restrict__ scalar) {
+    double s = *scalar;
+    if (s == 0.0) return;
+    double inv = 1.0 / s;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= inv;
+}
+
+__global__ void sumsq_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* partial) {
+    __shared__ double red[RED_THREADS / 32];
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += a[i] * b[i];
+    s = block_sum_256(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void final_sum_kernel(const double* __restrict__ partial, int nparts, double* dst) {
+    __shared__ double red[RED_THREADS / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+    s = block_sum_256(s, red);
+    if (threadIdx.x == 0) *dst = s;
+}
+
+__global__ void scale_by_inv_norm_kernel(double* __restrict__ x, size_t n, const double* __restrict__ sumsq) {
+    double s = *sumsq;
+    if (!(s > 0.0)) return;
+    double inv = 1.0 / sqrt(s);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= inv;
+}
+
+__global__ void gather5_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t d1, int64_t d2, int64_t d3,
+                               int64_t d4, int64_t s0, int64_t s1, int64_t s2, int64_t s3, int64_t s4, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        int64_t i4 = r % d4; r /= d4;
+        int64_t i3 = r % d3; r /= d3;
+        int64_t i2 = r % d2; r /= d2;
+        int64_t i1 = r % d1; r /= d1;
+        int64_t i0 = (int64_t)r;
+        dst[i] = src[i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3 + i4 * s4];
+    }
+}
+
+__global__ void scale_cols_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                                  const double* __restrict__ w, int64_t nrows, int ncols) {
+    size_t total = (size_t)nrows * ncols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ncols;
+        int c = (int)(i - r * ncols);
+        double v = src[r * lds + c];
+        dst[r * ldd + c] = w ? v * w[c] : v;
+    }
+}
+
+__global__ void inv_sqrt_weights_kernel(const double* __restrict__ S, double* __restrict__ w, int ncols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncols) w[i] = 1.0 / sqrt(S[i] / S[0]);
+}
+
+static inline int blocks_for(size_t n, int per_thread = 1) {
+    size_t b = (n + (size_t)RED_THREADS * per_thread - 1) / ((size_t)RED_THREADS * per_thread);
+    if (b < 1) b = 1;
+    if (b > (size_t)RED_BLOCKS) b = RED_BLOCKS;
+    return (int)b;
+}
+
+int absmax_launch(const double* x, size_t n, double* dst, cudaStream_t s) {
+    if (n == 0) return OK;
+    absmax_kernel<<<blocks_for(n, 8), RED_THREADS, 0, s>>>(x, n, dst);
+    AB_LAUNCHED();
+    return OK;
+}
+int scale_inv_launch(double* x, size_t n, const double* scalar, cudaStream_t s) {
+    if (n == 0) return OK;
+    scale_inv_kernel<<<blocks_for(n, 4), RED_THREADS, 0, s>>>(x, n, scalar);
+    AB_LAUNCHED();
+    return OK;
+}
+size_t frob_scratch_doubles() { return RED_BLOCKS + 8; }
+int dot_launch(const double* a, const double* b, size_t n, double* dst, double* scratch, cudaStream_t s) {
+    int nb = blocks_for(n, 8);
+    sumsq_partial_kernel<<<nb, RED_THREADS, 0, s>>>(a, b, n, scratch);
+    AB_LAUNCHED();
+    final_sum_kernel<<<1, RED_THREADS, 0, s>>>(scratch, nb, dst);
+    AB_LAUNCHED();
+    return OK;
+}
+int frob_normalize_launch(double* x, size_t n, double* scratch, cudaStream_t s) {
+    if (n == 0) return OK;
+    double* total = scratch + RED_BLOCKS;
+    AB_TRY(dot_launch(x, x, n, total, scratch, s));
+    scale_by_inv_norm_kernel<<<blocks_for(n, 4), RED_THREADS, 0, s>>>(x, n, total);
+    AB_LAUNCHED();
+    return OK;
+}
+int gather5_launch(double* dst, const double* src, const int64_t dims[5], const int64_t st[5], cudaStream_t s) {
+    size_t total = (size_t)dims[0] * dims[1] * dims[2] * dims[3] * dims[4];
+    if (total == 0) return OK;
+    gather5_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, src, dims[1], dims[2], dims[3], dims[4], st[0], st[1], st[2],
+                                                           st[3], st[4], total);
+    AB_LAUNCHED();
+    return OK;
+}
+int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, int64_t nrows, int ncols,
+                      cudaStream_t s) {
+    size_t total = (size_t)nrows * ncols;
+    if (total == 0) return OK;
+    scale_cols_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, ldd, src, lds, w, nrows, ncols);
+    AB_LAUNCHED();
+    return OK;
+}
+int copy2d_launch(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t nrows, int ncols, cudaStream_t s) {
+    return scale_cols_launch(dst, ldd, src, lds, nullptr, nrows, ncols, s);
+}
+int inv_sqrt_weights_launch(const double* S, double* w, int ncols, cudaStream_t s) {
+    if (ncols <= 0) return OK;
+    inv_sqrt_weights_kernel<<<(ncols + 255) / 256, 256, 0, s>>>(S, w, ncols);
+    AB_LAUNCHED();
+    return OK;
+}
+
+}  // namespace ab200
+
+// ---- bench-only: live FP64 tensor-pipe roof (DMMA.8x8x4 issue-rate loop, no memory traffic) -------------------------
+namespace ab200 {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// returns the flop count of one launch; the caller times it with CUDA events
+double dmma_peak_launch(double* scratch, int iters, cudaStream_t s) {
+    int blocks = device_sm_count() * 2;
+    dmma_peak_kernel<<<blocks, 256, 0, s>>>(scratch, iters);
+    return 2.0 * 256.0 * 8.0 * (double)iters * 8.0 * blocks;
+}
+}  // namespace ab200

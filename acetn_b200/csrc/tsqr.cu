@@ -1,0 +1,236 @@
+// K4: orthonormal basis of a tall-skinny matrix (the QR steps of the randomized SVD, reference
+// acetn/linalg/fused_matmul_svd_lowrank.py:38,43; only the Q factor is ever used there).
+//
+// Block classical Gram-Schmidt with re-orthogonalisation (BCGS2) over 32-column panels; the inter-panel
+// projections are two K1 DGEMMs each, the intra-panel factorisation is a Householder TSQR:
+//   level 0: every 256-row chunk is factored in shared memory (reflectors stay in place, R goes to a stack),
+//   level l: the stack of R factors is factored the same way until one chunk is left,
+//   then the explicit Q is formed top-down by applying the stored reflectors to [M;0] blocks.
+// Householder keeps ||Q^T Q - I|| at machine precision for any conditioning of Y (CholeskyQR would lose the
+// trailing directions of the power-iterated Y, SURVEY.md section 7 hard part 2).
+#include "kernels.cuh"
+
+namespace ab200 {
+
+constexpr int TS_CH = 256;   // rows per chunk (one thread per row)
+constexpr int TS_PB = 32;    // panel width
+constexpr int TS_NW = TS_CH / 32;
+
+// Factor one chunk: P[r0:r0+rows, 0:b] = H_0 ... H_{b-1} [R; 0].  Reflectors overwrite the strictly lower part of P.
+__global__ void __launch_bounds__(TS_CH, 1)
+tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
+                   double* __restrict__ tau_out) {
+    extern __shared__ double sm[];
+    double* S = sm;                       // column major: S[c*TS_CH + r]
+    double* tau_s = sm + TS_PB * TS_CH;   // [TS_PB]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
+    const int nref = b < rows ? b : rows;
+
+    for (int idx = tid; idx < rows * b; idx += TS_CH) {
+        int r = idx / b, c = idx - r * b;
+        S[c * TS_CH + r] = P[(r0 + r) * ld + c];
+    }
+    if (tid < TS_PB) tau_s[tid] = 0.0;
+    __syncthreads();
+
+    // builds the reflector of column c from rows >= c (one full warp)
+    auto prepare = [&](int c) {
+        double* col = S + c * TS_CH;
+        double ss = 0.0;
+        for (int r = c + 1 + lane; r < rows; r += 32) ss += col[r] * col[r];
+        ss = warp_sum(ss);
+        double alpha = col[c];
+        double tau = 0.0, beta = alpha, scale = 0.0;
+        if (ss != 0.0) {
+            double nrm = sqrt(alpha * alpha + ss);
+            beta = alpha >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        for (int r = c + 1 + lane; r < rows; r += 32) col[r] *= scale;
+        __syncwarp();
+        if (lane == 0) { col[c] = beta; tau_s[c] = tau; }
+    };
+
+    if (warp == 0 && nref > 0) prepare(0);
+    __syncthreads();
+    for (int j = 0; j < nref; j++) {
+        const double tau = tau_s[j];
+        const double* vcol = S + j * TS_CH;
+        for (int c = j + 1 + warp; c < b; c += TS_NW) {
+            double* col = S + c * TS_CH;
+            double dot = 0.0;
+            for (int r = j + 1 + lane; r < rows; r += 32) dot += vcol[r] * col[r];
+            dot = (warp_sum(dot) + col[j]) * tau;
+            __syncwarp();
+            for (int r = j + 1 + lane; r < rows; r += 32) col[r] -= vcol[r] * dot;
+            if (lane == 0) col[j] -= dot;
+            __syncwarp();
+            if (c == j + 1 && c < nref) prepare(c);
+        }
+        __syncthreads();
+    }
+    // reflectors (and R) back to P; R block (b x b, zero below the diagonal / beyond rows) to the stack
+    for (int idx = tid; idx < rows * b; idx += TS_CH) {
+        int r = idx / b, c = idx - r * b;
+        P[(r0 + r) * ld + c] = S[c * TS_CH + r];
+    }
+    for (int idx = tid; idx < b * b; idx += TS_CH) {
+        int i = idx / b, c = idx - i * b;
+        Rstack[((int64_t)blockIdx.x * b + i) * b + c] = (i <= c && i < nref) ? S[c * TS_CH + i] : 0.0;
+    }
+    if (tid < b) tau_out[(int64_t)blockIdx.x * b + tid] = tau_s[tid];
+}
+
+// Form the explicit Q rows of one chunk: Q_chunk = H_0 ... H_{b-1} [M; 0], M = Min rows [chunk*b, chunk*b + b) (identity if null).
+__global__ void __launch_bounds__(TS_CH, 1)
+tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
+                  const double* __restrict__ Min) {
+    extern __shared__ double sm[];
+    double* S = sm;                        // reflectors, column major
+    double* Z = sm + TS_PB * TS_CH;        // result, column major
+    double* tau_s = Z + TS_PB * TS_CH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
+    const int nref = b < rows ? b : rows;
+
+    for (int idx = tid; idx < rows * b; idx += TS_CH) {
+        int r = idx / b, c = idx - r * b;
+        S[c * TS_CH + r] = P[(r0 + r) * ld + c];
+        double z = 0.0;
+        if (r < nref) z = Min ? Min[((int64_t)blockIdx.x * b + r) * b + c] : (r == c ? 1.0 : 0.0);
+        Z[c * TS_CH + r] = z;
+    }
+    if (tid < TS_PB) tau_s[tid] = tid < b ? tau_in[(int64_t)blockIdx.x * b + tid] : 0.0;
+    __syncthreads();
+
+    // each warp owns columns c = warp, warp+8, ... of Z; no cross-warp dependency
+    for (int j = nref - 1; j >= 0; j--) {
+        const double tau = tau_s[j];
+        if (tau == 0.0) continue;
+        const double* vcol = S + j * TS_CH;
+        for (int c = warp; c < b; c += TS_NW) {
+            double* zc = Z + c * TS_CH;
+            double dot = 0.0;
+            for (int r = j + 1 + lane; r < rows; r += 32) dot += vcol[r] * zc[r];
+            dot = (warp_sum(dot) + zc[j]) * tau;
+            __syncwarp();
+            for (int r = j + 1 + lane; r < rows; r += 32) zc[r] -= vcol[r] * dot;
+            if (lane == 0) zc[j] -= dot;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rows * b; idx += TS_CH) {
+        int r = idx / b, c = idx - r * b;
+        P[(r0 + r) * ld + c] = Z[c * TS_CH + r];
+    }
+}
+
+namespace {
+constexpr size_t FACTOR_SMEM = (size_t)(TS_PB * TS_CH + TS_PB) * sizeof(double);
+constexpr size_t APPLY_SMEM = (size_t)(2 * TS_PB * TS_CH + TS_PB) * sizeof(double);
+
+struct Levels {
+    int n;
+    int64_t rows[8];
+    int64_t chunks[8];
+};
+Levels plan_levels(int64_t m, int b) {
+    Levels L; L.n = 0;
+    int64_t rows = m;
+    while (true) {
+        int64_t ch = (rows + TS_CH - 1) / TS_CH;
+        L.rows[L.n] = rows; L.chunks[L.n] = ch; L.n++;
+        if (ch == 1 || L.n == 8) break;
+        rows = ch * b;
+    }
+    return L;
+}
+size_t tsqr_scratch_doubles(int64_t m) {
+    Levels L = plan_levels(m, TS_PB);
+    size_t tot = 0;
+    for (int l = 0; l < L.n; l++) tot += (size_t)L.chunks[l] * TS_PB * TS_PB + (size_t)L.chunks[l] * TS_PB + 64;
+    return tot;
+}
+
+// orthonormalise one panel P (m x b, leading dimension ld) in place
+int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FACTOR_SMEM));
+        AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
+        configured = true;
+    }
+    Levels L = plan_levels(m, b);
+    double* mat[9]; int64_t lds[9]; double* rst[8]; double* tau[8];
+    mat[0] = P; lds[0] = ld;
+    double* cur = scratch;
+    for (int l = 0; l < L.n; l++) {
+        rst[l] = cur; cur += (size_t)L.chunks[l] * b * b;
+        tau[l] = cur; cur += (size_t)L.chunks[l] * b + 64 - ((size_t)L.chunks[l] * b) % 2;
+        mat[l + 1] = rst[l]; lds[l + 1] = b;
+    }
+    for (int l = 0; l < L.n; l++) {
+        tsqr_factor_kernel<<<(unsigned)L.chunks[l], TS_CH, FACTOR_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, rst[l], tau[l]);
+        AB_LAUNCHED();
+    }
+    for (int l = L.n - 1; l >= 0; l--) {
+        const double* Min = (l == L.n - 1) ? nullptr : mat[l + 1];
+        tsqr_apply_kernel<<<(unsigned)L.chunks[l], TS_CH, APPLY_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, tau[l], Min);
+        AB_LAUNCHED();
+    }
+    return OK;
+}
+
+GemmDesc proj_coeff_desc(const double* Y, int64_t ld, int64_t m, int j0, int b, double* Sc) {
+    // Sc[i][c] = sum_r Y[r][i] * Y[r][j0 + c]
+    return gemm_desc(j0, b, (int)m, operand(Y, idx1(1), idx1(ld)), operand(Y + j0, idx1(ld), idx1(1)), Sc, idx1(b), idx1(1));
+}
+GemmDesc proj_update_desc(double* Y, int64_t ld, int64_t m, int j0, int b, const double* Sc) {
+    // P[r][c] -= sum_i Y[r][i] * Sc[i][c]
+    return gemm_desc((int)m, b, j0, operand(Y, idx1(ld), idx1(1)), operand(Sc, idx1(b), idx1(1)), Y + j0, idx1(ld), idx1(1), -1.0, 1.0);
+}
+}  // namespace
+
+size_t orthonormalize_workspace_bytes(int64_t m, int q) {
+    size_t bytes = ws_round(tsqr_scratch_doubles(m) * sizeof(double));
+    bytes += ws_round((size_t)q * TS_PB * sizeof(double));
+    size_t g = 0;
+    for (int j0 = TS_PB; j0 < q; j0 += TS_PB) {
+        int b = (q - j0) < TS_PB ? (q - j0) : TS_PB;
+        size_t a = gemm_workspace_bytes(proj_coeff_desc(nullptr, q, m, j0, b, nullptr));
+        size_t c = gemm_workspace_bytes(proj_update_desc(nullptr, q, m, j0, b, nullptr));
+        if (a > g) g = a;
+        if (c > g) g = c;
+    }
+    return bytes + g + 1024;
+}
+
+int orthonormalize_launch(double* Y, int64_t m, int q, int64_t ld, void* wsp, size_t ws_bytes, cudaStream_t s) {
+    AB_REQUIRE(q >= 1 && m >= q, "orthonormalize: need m >= q >= 1 (m=%lld q=%d)", (long long)m, q);
+    AB_REQUIRE(m < 2147483647LL, "orthonormalize: m too large");
+    Workspace ws(wsp, ws_bytes);
+    double* scratch = ws.take<double>(tsqr_scratch_doubles(m));
+    double* Sc = ws.take<double>((size_t)q * TS_PB);
+    if (ws.overflow) { set_error("orthonormalize: workspace too small"); return ERR_WORKSPACE; }
+    void* gws = ws.base + ws.used;
+    size_t gws_bytes = ws.bytes - ws.used;
+    for (int j0 = 0; j0 < q; j0 += TS_PB) {
+        int b = (q - j0) < TS_PB ? (q - j0) : TS_PB;
+        for (int pass = 0; pass < 2; pass++) {
+            if (j0 == 0 && pass == 1) break;   // the first panel has nothing to be re-orthogonalised against
+            if (j0 > 0) {
+                AB_TRY(gemm_launch(proj_coeff_desc(Y, ld, m, j0, b, Sc), gws, gws_bytes, s));
+                AB_TRY(gemm_launch(proj_update_desc(Y, ld, m, j0, b, Sc), gws, gws_bytes, s));
+            }
+            AB_TRY(tsqr_panel(Y + j0, m, b, ld, scratch, s));
+        }
+    }
+    return OK;
+}
+
+}  // namespace ab200

@@ -1,0 +1,242 @@
+"""Tensor-level wrappers around the C ABI: allocate outputs/workspace with torch, pass raw pointers, extents,
+strides and the current CUDA stream.  No torch types cross the boundary."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_workspaces = {}
+_initialised = set()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        if t.dtype != torch.float64:
+            raise RuntimeError(f"acetn_b200: only float64 is supported on the b200 backend (got {t.dtype})")
+    dev = tensors[0].device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _initialised:
+        with torch.cuda.device(idx):
+            _lib.check(_lib.load().acetn_b200_init(idx), "init")
+        _initialised.add(idx)
+    return dev
+
+
+def _ws(dev, nbytes):
+    """Per-device grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _workspaces[key] = None
+        buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspace():
+    _workspaces.clear()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def launch_count():
+    return int(_lib.load().acetn_b200_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().acetn_b200_reset_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def gemm_ex(M, N, K, batch, A, B, C, idx, alpha=1.0, beta=0.0, force_tile=0, force_splitk=0):
+    """Raw K1 call. idx: 27 ints = {div,s_hi,s_lo} for A(m,k,batch), B(k,n,batch), C(m,n,batch)."""
+    dev = _require_cuda(A, B, C)
+    lib = _lib.load()
+    ix = _lib.i64_array(idx)
+    nb = lib.acetn_b200_gemm_workspace_bytes(M, N, K, batch, ix, force_tile, force_splitk)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_gemm(M, N, K, batch, _p(A), _p(B), _p(C), ix, float(alpha), float(beta), force_tile, force_splitk,
+                                 _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "gemm")
+    return C
+
+
+def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0):
+    """C = op(A) @ B for 2-D row-major tensors through K1 (test/bench convenience)."""
+    A = A.contiguous()
+    B = B.contiguous()
+    if transpose_a:
+        K, M = A.shape
+        a_idx = [0, 0, 1, 0, 0, M, 0, 0, 0]
+    else:
+        M, K = A.shape
+        a_idx = [0, 0, K, 0, 0, 1, 0, 0, 0]
+    N = B.shape[1]
+    C = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    idx = a_idx + [0, 0, N, 0, 0, 1, 0, 0, 0] + [0, 0, N, 0, 0, 1, 0, 0, 0]
+    return gemm_ex(M, N, K, 1, A, B, C, idx, force_tile=force_tile, force_splitk=force_splitk)
+
+
+def quarter_tensor(C, E2, E1, A_view, normalize=True):
+    """projectors.py:36-60.  C (xa,xb), E2 (xb,xc,D,D), E1 (xe,xa,D,D), A_view = bond_permute(k) (strided view)."""
+    dev = _require_cuda(C, E2, E1, A_view)
+    C, E2, E1 = C.contiguous(), E2.contiguous(), E1.contiguous()
+    xa, xb = C.shape
+    xc, D = E2.shape[1], E2.shape[2]
+    xe = E1.shape[0]
+    d = A_view.shape[4]
+    if E2.shape[0] != xb or E1.shape[1] != xa:
+        raise ValueError(f"quarter_tensor: inconsistent chi legs C{tuple(C.shape)} E2{tuple(E2.shape)} E1{tuple(E1.shape)}")
+    lib = _lib.load()
+    Q = torch.empty(xc * D * D, xe * D * D, dtype=torch.float64, device=dev)
+    nb = lib.acetn_b200_quarter_tensor_workspace_bytes(xa, xb, xc, xe, D, d)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_quarter_tensor(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
+                                           1 if normalize else 0, _p(Q), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "quarter_tensor")
+    return Q, (xc, D, D, xe, D, D)
+
+
+def orthonormalize(Y):
+    """In-place orthonormal basis of range(Y) (torch.linalg.qr(Y).Q up to column signs/rotations)."""
+    dev = _require_cuda(Y)
+    assert Y.dim() == 2 and Y.is_contiguous()
+    m, q = Y.shape
+    lib = _lib.load()
+    nb = lib.acetn_b200_orthonormalize_workspace_bytes(m, q)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_orthonormalize(_p(Y), m, q, q, _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "orthonormalize")
+    return Y
+
+
+def jacobi_svd(R, chi=None, cutoff=0.0):
+    """R (q,q) = Jt^T diag(S) Wt. Returns S, Wt, Jt, info(int32[2])."""
+    dev = _require_cuda(R)
+    R = R.contiguous()
+    q = R.shape[0]
+    lib = _lib.load()
+    S = torch.empty(q, dtype=torch.float64, device=dev)
+    Wt = torch.empty(q, q, dtype=torch.float64, device=dev)
+    Jt = torch.empty(q, q, dtype=torch.float64, device=dev)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    nb = lib.acetn_b200_jacobi_svd_workspace_bytes(q)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_jacobi_svd(_p(R), q, _p(S), _p(Wt), _p(Jt), q if chi is None else chi, float(cutoff), _p(info),
+                                       _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "jacobi_svd")
+    return S, Wt, Jt, info
+
+
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12):
+    """Randomized SVD of mats[0] @ ... @ mats[-1] with the caller's test matrix omega (n, q).
+    Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps])."""
+    dev = _require_cuda(*mats, omega)
+    mats = [m.contiguous() for m in mats]
+    omega = omega.contiguous()
+    nmat = len(mats)
+    rows = [m.shape[0] for m in mats]
+    cols = [m.shape[1] for m in mats]
+    n, q = omega.shape
+    if n != cols[-1]:
+        raise ValueError("rsvd: omega rows must equal the column count of the last factor")
+    m = rows[0]
+    lib = _lib.load()
+    U = torch.empty(m, q, dtype=torch.float64, device=dev)
+    S = torch.empty(q, dtype=torch.float64, device=dev)
+    V = torch.empty(n, q, dtype=torch.float64, device=dev)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    r_arr, c_arr = _lib.i64_array(rows), _lib.i64_array(cols)
+    nb = lib.acetn_b200_rsvd_workspace_bytes(nmat, r_arr, c_arr, q)
+    ws = _ws(dev, nb)
+    ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() for t in mats])
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_rsvd(nmat, ptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
+                                 q if chi is None else int(chi), float(cutoff), _p(U), _p(S), _p(V), _p(info), _p(ws), ws.numel(),
+                                 _stream(dev))
+    _lib.check(st, "rsvd")
+    return U, S, V, info
+
+
+def projectors_from_usv(Q1, Q4, U, V, S, keep):
+    """projectors.py:166-173. Q1 (m1,n1), Q4 (m4,n4), U (m1,q), V (n4,q). Returns proj1 (n1,keep), proj2 (m4,keep)."""
+    dev = _require_cuda(Q1, Q4, U, V, S)
+    m1, n1 = Q1.shape
+    m4, n4 = Q4.shape
+    lib = _lib.load()
+    p1 = torch.empty(n1, keep, dtype=torch.float64, device=dev)
+    p2 = torch.empty(m4, keep, dtype=torch.float64, device=dev)
+    nb = lib.acetn_b200_projectors_workspace_bytes(m1, n1, m4, n4, keep)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_projectors_from_usv(_p(Q1), m1, n1, _p(Q4), m4, n4, _p(U), U.stride(0), _p(V), V.stride(0), _p(S), keep,
+                                                _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "projectors_from_usv")
+    return p1, p2
+
+
+def absorb_corner1(ci, ei, proj):
+    """directional_mover.py:306-323 : out[a,x]."""
+    dev = _require_cuda(ci, ei, proj)
+    ci, ei, proj = ci.contiguous(), ei.contiguous(), proj.contiguous()
+    xa, xb, D = ei.shape[0], ei.shape[1], ei.shape[2]
+    xc, xx = ci.shape[1], proj.shape[3]
+    if ci.shape[0] != xb or proj.shape[0] != xc:
+        raise ValueError("absorb_corner1: inconsistent chi legs")
+    lib = _lib.load()
+    out = torch.empty(xa, xx, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_absorb_corner_workspace_bytes(xa, xb, xc, xx, D))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_absorb_corner1(_p(ci), _p(ei), _p(proj), xa, xb, xc, xx, D, _p(out), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "absorb_corner1")
+    return out
+
+
+def absorb_corner2(ci, ei, proj):
+    """directional_mover.py:325-343 : out[x,c]."""
+    dev = _require_cuda(ci, ei, proj)
+    ci, ei, proj = ci.contiguous(), ei.contiguous(), proj.contiguous()
+    xa, xb = ci.shape
+    xc, D = ei.shape[1], ei.shape[2]
+    xx = proj.shape[3]
+    if ei.shape[0] != xb or proj.shape[0] != xa:
+        raise ValueError("absorb_corner2: inconsistent chi legs")
+    lib = _lib.load()
+    out = torch.empty(xx, xc, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_absorb_corner_workspace_bytes(xa, xb, xc, xx, D))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_absorb_corner2(_p(ci), _p(ei), _p(proj), xa, xb, xc, xx, D, _p(out), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "absorb_corner2")
+    return out
+
+
+def absorb_edge(ei, A_view, proj2, proj1):
+    """directional_mover.py:345-366 : out[y,x,r,R]."""
+    dev = _require_cuda(ei, A_view, proj2, proj1)
+    ei, proj1, proj2 = ei.contiguous(), proj1.contiguous(), proj2.contiguous()
+    xa, xb, D = ei.shape[0], ei.shape[1], ei.shape[2]
+    d = A_view.shape[4]
+    xx, xy = proj1.shape[3], proj2.shape[3]
+    if proj1.shape[0] != xb or proj2.shape[0] != xa:
+        raise ValueError("absorb_edge: inconsistent chi legs")
+    lib = _lib.load()
+    out = torch.empty(xy, xx, D, D, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_absorb_edge_workspace_bytes(xa, xb, xx, xy, D, d))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_absorb_edge(_p(ei), _p(A_view), _lib.i64_array(A_view.stride()), _p(proj2), _p(proj1), xa, xb, xx, xy, D, d,
+                                        _p(out), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "absorb_edge")
+    return out

@@ -1,0 +1,143 @@
+/*
+ * acetn_b200.h -- C ABI of libacetn_b200.so: the B200 (sm_100a) implementation of Ace-TN's CTMRG hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one reference call site
+ * (cited per function; paths relative to the ace-tn repository root) and is what a ctypes / pybind / cgo stub
+ * on the reference side binds.
+ *
+ * Conventions
+ *   - all tensors are FP64, row-major contiguous device memory unless a stride array is taken;
+ *   - one int64 extent per tensor leg (chi legs may differ between tensors);
+ *   - the caller owns all memory, including the scratch workspace: query *_workspace_bytes(), allocate
+ *     (torch.empty on the host side), pass pointer + size;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device
+ *     or allocates device memory;
+ *   - every function returns 0 on success; on failure a non-zero ACETN_B200_ERR_* code and
+ *     acetn_b200_last_error() holds a message (thread local).  Nothing throws across the boundary.
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points fail with ACETN_B200_ERR_CUDA.
+ *
+ * Index names follow the reference's einsum strings so the two can be read side by side.
+ * Bond direction k: 0=left 1=up 2=right 3=down; A[l,u,r,d,p]; C[k] (chi,chi); E[k] (chi,chi,D,D).
+ */
+#ifndef ACETN_B200_H
+#define ACETN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACETN_B200_OK 0
+#define ACETN_B200_ERR_INVALID 1
+#define ACETN_B200_ERR_WORKSPACE 2
+#define ACETN_B200_ERR_CUDA 3
+#define ACETN_B200_ERR_UNSUPPORTED 4
+
+/* ---- library lifetime (replaces the function-local static cuTENSOR/cuSOLVER handle singletons,
+ *      csrc/linalg/contraction.h:76-94, csrc/linalg/cholesky_solve.h:12-30) ------------------------------ */
+int acetn_b200_init(int device);
+int acetn_b200_destroy(void);
+const char* acetn_b200_last_error(void);
+const char* acetn_b200_version(void);
+/* number of kernel launches issued by this library in the calling process since the last reset */
+int64_t acetn_b200_launch_count(void);
+void acetn_b200_reset_launch_count(void);
+
+/* ---- K1: general two-level-index FP64 DMMA GEMM (the primitive behind every torch.einsum / @ of the path;
+ *      replaces cuTENSOR's TTGT contraction, csrc/linalg/contraction.h:96-309) ---------------------------------
+ * C(m,n)[b] = alpha * sum_k A(m,k)[b] B(k,n)[b] + beta * C(m,n)[b]
+ * Each index group g of each operand is described by 3 int64: {div, s_hi, s_lo}:
+ *      offset(i) = div ? (i / div) * s_hi + (i % div) * s_lo : i * s_lo.
+ * idx = 27 int64: A{row=m, col=k, batch}, B{row=k, col=n, batch}, C{m, n, batch}. */
+size_t acetn_b200_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, const int64_t* idx,
+                                       int force_tile, int force_splitk);
+int acetn_b200_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, const double* A, const double* B, double* C,
+                    const int64_t* idx, double alpha, double beta, int force_tile, int force_splitk, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- quarter tensor: ProjectorCalculator.make_quarter_tensor, acetn/renormalization/projectors.py:36-60 -----
+ *   Q[(c,r,R),(e,d,D)] = sum C[a,b] E2[b,c,u,U] E1[e,a,l,L] conj(A)[L,U,R,D,P] A[l,u,r,d,P],  then Q /= max|Q|
+ *   C  (chi_a, chi_b) = site.C[k];  E2 (chi_b, chi_c, D, D) = site.E[k];  E1 (chi_e, chi_a, D, D) = site.E[(3+k)%4]
+ *   A  = site.bond_permute(k), a strided view: a_strides[5] in elements for legs (l,u,r,d,p) of the view.
+ *   Q out: (chi_c*D*D) x (chi_e*D*D) row-major.  normalize != 0 applies the max-abs division (projectors.py:59). */
+size_t acetn_b200_quarter_tensor_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_e,
+                                                 int64_t D, int64_t d);
+int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E1, const double* A,
+                              const int64_t* a_strides, int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_e,
+                              int64_t D, int64_t d, int normalize, double* Q, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- randomized SVD family: acetn/linalg/{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}.py
+ *   rSVD of the product M_0 M_1 ... M_{nmat-1} (nmat = 1, 2 or 4) without forming it.  mats[i] is rows[i] x cols[i]
+ *   row-major contiguous; Omega is (cols[nmat-1] x q), drawn by the caller with torch.randn exactly as the reference
+ *   does (fused_matmul_svd_lowrank.py:32) so both consume identical test matrices.
+ *   reorth_adjoint != 0 re-orthonormalises between the adjoint and forward halves of each power step
+ *   (fused_3matmul_svd_lowrank.py:39-45).
+ *   Outputs: U (rows[0] x q), S (q, descending), V (cols[nmat-1] x q)  [V not transposed, as the reference],
+ *   info (device int32[2]): info[0] = min(chi, #{S/S[0] > cutoff})  (projectors.py:163-164), info[1] = Jacobi sweeps. */
+size_t acetn_b200_rsvd_workspace_bytes(int nmat, const int64_t* rows, const int64_t* cols, int64_t q);
+int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, const int64_t* cols, const double* Omega,
+                    int64_t q, int niter, int reorth_adjoint, int64_t chi, double cutoff, double* U, double* S,
+                    double* V, int32_t* info, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- orthonormal basis of a tall matrix (torch.linalg.qr(Y).Q, fused_matmul_svd_lowrank.py:38,43), in place */
+size_t acetn_b200_orthonormalize_workspace_bytes(int64_t m, int64_t q);
+int acetn_b200_orthonormalize(double* Y, int64_t m, int64_t q, int64_t ld, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- SVD of a small square matrix R (q x q): R = Jt^T diag(S) Wt  (torch.linalg.svd core) -------------------- */
+size_t acetn_b200_jacobi_svd_workspace_bytes(int64_t q);
+int acetn_b200_jacobi_svd(const double* R, int64_t q, double* S, double* Wt, double* Jt, int64_t chi, double cutoff,
+                          int32_t* info, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- projector formation: projectors.py:166-173 (half-system) ---------------------------------------------------
+ *   proj1[(e,d,D), z] = sum_x Q1[x,(e,d,D)] U[x,z] w[z],  proj2[(c,u,U), z] = sum_y Q4[(c,u,U),y] V[y,z] w[z],
+ *   w[z] = (S[z]/S[0])^-1/2, z < keep.   Q1: m1 x n1, Q4: m4 x n4, U: m1 x ldu, V: n4 x ldv.
+ *   proj1 out: n1 x keep, proj2 out: m4 x keep. */
+size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep);
+int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
+                                   const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S,
+                                   int64_t keep, double* proj1, double* proj2, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- absorption: DirectionalMover.renormalize_cj1/cj2/ej, acetn/renormalization/directional_mover.py:306-366 ---
+ *   corner1: out[a,x] = sum ei[a,b,l,L] ci[b,c] proj[c,l,L,x] / ||.||     ci (chi_b,chi_c) ei (chi_a,chi_b,D,D) proj (chi_c,D,D,chi_x)
+ *   corner2: out[x,c] = sum proj[a,r,R,x] ci[a,b] ei[b,c,r,R] / ||.||     ci (chi_a,chi_b) ei (chi_b,chi_c,D,D) proj (chi_a,D,D,chi_x)
+ *   edge   : out[y,x,r,R] = sum ei[a,b,l,L] proj1[b,u,U,x] conj(A)[L,U,R,D,P] A[l,u,r,d,P] proj2[a,d,D,y] / ||.||
+ *            ei (chi_a,chi_b,D,D), proj1 (chi_b,D,D,chi_x), proj2 (chi_a,D,D,chi_y), A = bond_permute(k) view. */
+size_t acetn_b200_absorb_corner_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_x, int64_t D);
+int acetn_b200_absorb_corner1(const double* ci, const double* ei, const double* proj, int64_t chi_a, int64_t chi_b,
+                              int64_t chi_c, int64_t chi_x, int64_t D, double* out, void* ws, size_t ws_bytes,
+                              void* stream);
+int acetn_b200_absorb_corner2(const double* ci, const double* ei, const double* proj, int64_t chi_a, int64_t chi_b,
+                              int64_t chi_c, int64_t chi_x, int64_t D, double* out, void* ws, size_t ws_bytes,
+                              void* stream);
+size_t acetn_b200_absorb_edge_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_x, int64_t chi_y, int64_t D,
+                                              int64_t d);
+int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_strides, const double* proj2,
+                           const double* proj1, int64_t chi_a, int64_t chi_b, int64_t chi_x, int64_t chi_y, int64_t D,
+                           int64_t d, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- double-layer site absorption on its own (K2; the `cuUelL,LURDP->cuelRDP` + `lurdp,cuelRDp->crRedD` pair of
+ *      projectors.py:54-55 and the matching pair of directional_mover.py:363-364), exposed for tests/benchmarks.
+ *   in : X[b0, (i0,I0), b1, (i1,I1)] with block (b0,b1) at  b0*in_s0 + b1*in_s1 and element strides in_es[4] for
+ *        (i0,I0,i1,I1) = the ket/bra legs contracted with the first two legs (l,u) / (L,U) of A in `order`:
+ *        order 0: (i0,I0)=(u,U) , (i1,I1)=(l,L)   (quarter tensor);  order 1: (i0,I0)=(l,L), (i1,I1)=(u,U)   (edge)
+ *   out: Y[block][(r,R) , (d,D)] with element strides out_es[4] for (r,R,d,D) and block strides out_s0,out_s1. */
+size_t acetn_b200_double_layer_workspace_bytes(int64_t n0, int64_t n1, int64_t D, int64_t d);
+int acetn_b200_double_layer(const double* X, int64_t n0, int64_t n1, int64_t in_s0, int64_t in_s1,
+                            const int64_t* in_es, int order, const double* A, const int64_t* a_strides, int64_t D,
+                            int64_t d, double* Y, int64_t out_s0, int64_t out_s1, const int64_t* out_es, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* ---- bench-only: launches a register-resident DMMA.8x8x4 loop on every SM and returns its flop count; timed by the
+ *      caller with CUDA events it gives the live FP64 tensor-pipe roof used as the roofline denominator ---------- */
+double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream);
+
+/* ---- small helpers used by the host shim ------------------------------------------------------------------------ */
+int acetn_b200_absmax(const double* x, int64_t n, double* out_scalar_zeroed, void* stream);
+int acetn_b200_frob_normalize(double* x, int64_t n, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACETN_B200_H */

@@ -1,0 +1,217 @@
+"""GPU parity tests of the individual kernels behind the C ABI (K1 GEMM, K4 TSQR, K5 Jacobi, rSVD, quarter tensor,
+projectors, absorption) against torch fp64 / the CPU oracle on identical seeded inputs."""
+import pytest
+import torch
+
+from oracle import ctmrg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from acetn_b200 import ops
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, dtype=torch.float64, generator=g).to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- K1 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (129, 131, 67), (256, 258, 1000), (1000, 88, 515), (64, 64, 16),
+                                   (7, 5, 3), (300, 33, 2048), (512, 264, 4096)])
+@pytest.mark.parametrize("tile", [0, 1, 2, 3])
+def test_gemm_nn(M, N, K, tile):
+    A, B = rnd(M, K, seed=1), rnd(K, N, seed=2)
+    C = ops.matmul(A, B, force_tile=tile)
+    assert rel(C, A @ B) < 1e-13
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (130, 90, 77), (258, 258, 4096), (1024, 32, 256)])
+@pytest.mark.parametrize("tile", [1, 2, 3])
+def test_gemm_tn(M, N, K, tile):
+    A, B = rnd(K, M, seed=3), rnd(K, N, seed=4)
+    C = ops.matmul(A, B, transpose_a=True, force_tile=tile)
+    assert rel(C, A.T @ B) < 1e-13
+
+
+@pytest.mark.parametrize("splitk", [2, 3, 7])
+def test_gemm_splitk(splitk):
+    A, B = rnd(200, 3000, seed=5), rnd(3000, 150, seed=6)
+    C = ops.matmul(A, B, force_splitk=splitk)
+    assert rel(C, A @ B) < 1e-13
+
+
+def test_gemm_b_kcontig_and_beta():
+    # C = alpha * A @ Bt^T + beta * C with Bt stored (N, K)
+    M, N, K = 150, 70, 333
+    A, Bt, C0 = rnd(M, K, seed=7), rnd(N, K, seed=8), rnd(M, N, seed=9)
+    C = C0.clone()
+    idx = [0, 0, K, 0, 0, 1, 0, 0, 0] + [0, 0, 1, 0, 0, K, 0, 0, 0] + [0, 0, N, 0, 0, 1, 0, 0, 0]
+    ops.gemm_ex(M, N, K, 1, A, Bt, C, idx, alpha=-0.5, beta=2.0)
+    assert rel(C, -0.5 * A @ Bt.T + 2.0 * C0) < 1e-13
+
+
+@pytest.mark.parametrize("D", [2, 3, 4])
+def test_gemm_two_level_and_batched(D):
+    # T2[(c,uU),(e,lL)] = sum_a T1[a,(c,uU)] E1[e,a,lL]  (projectors.py:53), two-level n index on B
+    xa, xc, xe = 11, 9, 10
+    D2 = D * D
+    T1, E1 = rnd(xa, xc * D2, seed=10), rnd(xe, xa, D, D, seed=11)
+    C = torch.empty(xc * D2, xe * D2, dtype=torch.float64, device=DEV)
+    idx = [0, 0, 1, 0, 0, xc * D2, 0, 0, 0] + [0, 0, D2, D2, xa * D2, 1, 0, 0, 0] + [0, 0, xe * D2, 0, 0, 1, 0, 0, 0]
+    ops.gemm_ex(xc * D2, xe * D2, xa, 1, T1, E1, C, idx)
+    ref = torch.einsum("am,eal->mel", T1, E1.reshape(xe, xa, D2)).reshape(xc * D2, xe * D2)
+    assert rel(C, ref) < 1e-13
+    # batched: C[b] = A[b] @ B[b]
+    nb, M, N, K = 13, 20, 24, 17
+    A, B = rnd(nb, M, K, seed=12), rnd(nb, K, N, seed=13)
+    Cb = torch.empty(nb, M, N, dtype=torch.float64, device=DEV)
+    idx = [0, 0, K, 0, 0, 1, 0, 0, M * K] + [0, 0, N, 0, 0, 1, 0, 0, K * N] + [0, 0, N, 0, 0, 1, 0, 0, M * N]
+    ops.gemm_ex(M, N, K, nb, A, B, Cb, idx)
+    assert rel(Cb, A @ B) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- K4 TSQR
+@pytest.mark.parametrize("m,q", [(300, 20), (1000, 64), (4097, 130), (16384, 258), (80, 22), (40, 40), (257, 33)])
+def test_orthonormalize_random(m, q):
+    Y0 = rnd(m, q, seed=20)
+    Q = ops.orthonormalize(Y0.clone())
+    eye = torch.eye(q, dtype=torch.float64, device=DEV)
+    assert float((Q.T @ Q - eye).abs().max()) < 5e-14
+    assert rel(Q @ (Q.T @ Y0), Y0) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["graded", "rank_deficient"])
+def test_orthonormalize_ill_conditioned(kind):
+    m, q = 2048, 96
+    U = torch.linalg.qr(rnd(m, q, seed=21)).Q
+    V = torch.linalg.qr(rnd(q, q, seed=22)).Q
+    if kind == "graded":
+        s = torch.logspace(0, -20, q, dtype=torch.float64, device=DEV)
+    else:
+        s = torch.cat([torch.ones(10, dtype=torch.float64, device=DEV), torch.zeros(q - 10, dtype=torch.float64, device=DEV)])
+    Y0 = (U * s) @ V.T
+    Q = ops.orthonormalize(Y0.clone())
+    eye = torch.eye(q, dtype=torch.float64, device=DEV)
+    assert float((Q.T @ Q - eye).abs().max()) < 1e-13
+    assert float((Q @ (Q.T @ Y0) - Y0).norm() / Y0.norm()) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- K5 Jacobi
+@pytest.mark.parametrize("q", [1, 2, 5, 22, 64, 129, 258])
+def test_jacobi_svd(q):
+    # the core handed to K5 is the triangular factor of a QR (acetn_b200 rsvd pipeline); condition number 1e9
+    G = rnd(q, q, seed=30) * torch.logspace(0, -9, q, dtype=torch.float64, device=DEV)[None, :]
+    R = torch.linalg.qr(G.cpu()).R.to(DEV).contiguous()
+    S, Wt, Jt, info = ops.jacobi_svd(R)
+    ref = torch.linalg.svdvals(R.cpu()).to(DEV)
+    assert float((S - ref).abs().max() / ref[0]) < 5e-14
+    assert torch.all(S[:-1] >= S[1:])
+    eye = torch.eye(q, dtype=torch.float64, device=DEV)
+    assert float((Wt @ Wt.T - eye).abs().max()) < 1e-13
+    assert float((Jt @ Jt.T - eye).abs().max()) < 1e-13
+    assert rel(Jt.T @ torch.diag(S) @ Wt, R) < 1e-13
+    assert 0 < int(info[1]) <= 15
+
+
+def test_jacobi_svd_dense_unpreconditioned():
+    """A dense core that is not QR-preconditioned needs more sweeps but must still converge."""
+    q = 64
+    R = rnd(q, q, seed=31) * torch.logspace(0, -6, q, dtype=torch.float64, device=DEV)[None, :]
+    S, Wt, Jt, info = ops.jacobi_svd(R)
+    ref = torch.linalg.svdvals(R.cpu()).to(DEV)
+    assert float((S - ref).abs().max() / ref[0]) < 5e-14
+    assert rel(Jt.T @ torch.diag(S) @ Wt, R) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- rSVD
+def test_rsvd_against_oracle_same_omega():
+    g = torch.Generator().manual_seed(40)
+    A = torch.randn(300, 200, dtype=torch.float64, generator=g)
+    B = torch.randn(200, 260, dtype=torch.float64, generator=g)
+    tape = orc.OmegaTape()
+    U0, S0, V0 = orc.fused_matmul_svd_lowrank(A, B, q=34, niter=2, omega_fn=tape)
+    U, S, V, info = ops.rsvd([A.to(DEV), B.to(DEV)], tape.tape[0].to(DEV), niter=2)
+    assert float((S.cpu() - S0).abs().max() / S0[0]) < 1e-10
+    eye = torch.eye(34, dtype=torch.float64, device=DEV)
+    assert float((U.T @ U - eye).abs().max()) < 1e-10
+    assert float((V.T @ V - eye).abs().max()) < 1e-10
+    # same subspaces / same reconstruction (gauge invariant)
+    assert rel((U * S) @ V.T, ((U0 * S0) @ V0.T).to(DEV)) < 1e-8
+
+
+@pytest.mark.parametrize("nmat", [1, 2, 4])
+def test_rsvd_low_rank_recovery(nmat):
+    """reference tests/unit/test_linalg.py:45-55,151-161,231-241 : exact recovery of low-rank inputs to 1e-10."""
+    g = torch.Generator().manual_seed(41)
+    low = (torch.randn(120, 6, dtype=torch.float64, generator=g) @ torch.randn(6, 90, dtype=torch.float64, generator=g)).to(DEV)
+    mats = [low]
+    if nmat >= 2:
+        mats.append(rnd(90, 100, seed=42))
+    if nmat == 4:
+        mats += [rnd(100, 80, seed=43), rnd(80, 70, seed=44)]
+    full = mats[0]
+    for m_ in mats[1:]:
+        full = full @ m_
+    omega = rnd(mats[-1].shape[1], 12, seed=45)
+    U, S, V, _ = ops.rsvd(mats, omega, niter=2, reorth_adjoint=(nmat == 4))
+    assert rel((U * S) @ V.T, full) < 1e-10
+    assert torch.all(S[:-1] >= S[1:])
+
+
+# ---------------------------------------------------------------------------------------------- quarter / absorb
+CASES = [(2, 8, 2, 0), (3, 12, 2, 1), (4, 16, 2, 2), (3, 10, 3, 3), (8, 16, 2, 4)]
+
+
+@pytest.mark.parametrize("D,chi,d,seed", CASES)
+def test_quarter_tensor(D, chi, d, seed):
+    cell = orc.random_cell(2, 2, D, chi, d, seed=seed)
+    st = cell[(0, 0)]
+    A = st.A.to(DEV)
+    for k in range(4):
+        ref, shp = orc.quarter_tensor(st, k)
+        ak = A.permute([(i + k) % 4 for i in range(4)] + [4])
+        Q, qD = ops.quarter_tensor(st.C[k % 4].to(DEV), st.E[k % 4].to(DEV), st.E[(3 + k) % 4].to(DEV), ak)
+        assert tuple(qD) == tuple(shp)
+        assert rel(Q.cpu(), ref) < 1e-13
+
+
+def test_quarter_tensor_ragged_chi():
+    """chi legs need not be equal."""
+    D, d = 3, 2
+    g = torch.Generator().manual_seed(5)
+    A = torch.rand(D, D, D, D, d, dtype=torch.float64, generator=g) - 0.5
+    C = torch.rand(7, 5, dtype=torch.float64, generator=g)
+    E2 = torch.rand(5, 6, D, D, dtype=torch.float64, generator=g)
+    E1 = torch.rand(4, 7, D, D, dtype=torch.float64, generator=g)
+    st = orc.Site(A, [C] * 4, [E2, E2, E2, E1])
+    ref, shp = orc.quarter_tensor(st, 0)
+    Q, qD = ops.quarter_tensor(C.to(DEV), E2.to(DEV), E1.to(DEV), A.to(DEV))
+    assert tuple(qD) == tuple(shp) == (6, D, D, 4, D, D)
+    assert rel(Q.cpu(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("D,chi,d,seed", CASES)
+def test_absorption(D, chi, d, seed):
+    cell = orc.random_cell(2, 2, D, chi, d, seed=seed)
+    st = cell[(0, 0)]
+    A = st.A.to(DEV)
+    g = torch.Generator().manual_seed(seed)
+    for k in range(4):
+        pj1 = torch.rand(chi, D, D, chi - 1, dtype=torch.float64, generator=g)
+        pj2 = torch.rand(chi, D, D, chi - 2, dtype=torch.float64, generator=g)
+        ak = A.permute([(i + k) % 4 for i in range(4)] + [4])
+        c1 = ops.absorb_corner1(st.C[(3 + k) % 4].to(DEV), st.E[(2 + k) % 4].to(DEV), pj1.to(DEV))
+        c2 = ops.absorb_corner2(st.C[k].to(DEV), st.E[k].to(DEV), pj2.to(DEV))
+        e = ops.absorb_edge(st.E[(3 + k) % 4].to(DEV), ak, pj2.to(DEV), pj1.to(DEV))
+        assert rel(c1.cpu(), orc.absorb_corner1(st.C[(3 + k) % 4], st.E[(2 + k) % 4], pj1)) < 1e-13
+        assert rel(c2.cpu(), orc.absorb_corner2(st.C[k], st.E[k], pj2)) < 1e-13
+        ref_e = orc.absorb_edge(st.E[(3 + k) % 4], st.bond_permute(k), pj2, pj1)
+        assert e.shape == ref_e.shape
+        assert rel(e.cpu(), ref_e) < 1e-13

@@ -36,3 +36,30 @@ def model_terms(model):
 
 def rel_err(a, b):
     return float((a - b).norm() / b.norm())
+
+
+class rotated_qr:
+    """Context manager: torch.linalg.qr returns Q @ G (G a fixed random orthogonal matrix) instead of Q.
+    Any orthonormal basis of range(Y) is mathematically equivalent inside the randomized SVD, so the oracle run
+    under this patch measures how far the *reference algorithm itself* moves under an equivalent re-implementation
+    of its QR step -- the reproducibility envelope that bounds what parity can be asked of a different QR kernel."""
+
+    def __init__(self, seed=1):
+        self.seed = seed
+
+    def __enter__(self):
+        import collections
+        self._real = torch.linalg.qr
+        QR = collections.namedtuple("QR", ["Q", "R"])
+        real, seed = self._real, self.seed
+
+        def qr(Y, mode="reduced"):
+            Q, R = real(Y, mode=mode)
+            g = torch.Generator().manual_seed(seed * 1000003 + Q.shape[0] * 7 + Q.shape[1])
+            G = real(torch.randn(Q.shape[1], Q.shape[1], dtype=Q.dtype, generator=g)).Q
+            return QR(Q @ G, G.mH @ R)
+        torch.linalg.qr = qr
+        return self
+
+    def __exit__(self, *exc):
+        torch.linalg.qr = self._real
