@@ -64,7 +64,16 @@ def run_oracle(cell, nsweep, tape=None, projectors="half-system"):
     return ref, rec["spectra"], t.tape
 
 
-def energy(cell, hb=H, hs=None):
+def bond_ham_for(d):
+    if d == 2:
+        return H
+    g = torch.Generator().manual_seed(99)
+    m = torch.randn(d * d, d * d, dtype=torch.float64, generator=g)
+    return 0.5 * (m + m.T)
+
+
+def energy(cell, hb=None, hs=None):
+    hb = bond_ham_for(cell.dims["phys"]) if hb is None else hb
     return float(orc.measure(cell, hb, hs)["Energy"])
 
 
