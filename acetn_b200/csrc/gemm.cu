@@ -22,6 +22,7 @@ struct GemmKernelParams {
     double alpha, beta;
     double* ws;          // split-K partials [batch*splitk][M][N] (dense) when splitk > 1
     int a_vec, b_vec;    // 16-byte loads allowed along the contiguous index
+    int fast;            // both k indices single-level and both operands vectorisable: pointer-increment loader
 };
 
 template <int BM, int BN, bool A_MC, bool B_KC>
@@ -187,6 +188,60 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
         }
     };
 
+
+    // ---- fast loader state (p.fast): one global pointer + one smem byte offset + byte count per 16-byte chunk; the k
+    //      advance is a single add per tile, so the steady-state loop issues ~4 instructions per chunk ------------------
+    const double* a_gp[A_CH];
+    uint32_t a_so[A_CH];
+    int a_nb[A_CH];
+    const double* b_gp[B_CH];
+    uint32_t b_so[B_CH];
+    int b_nb[B_CH];
+    const int64_t a_kstep = (int64_t)BK * p.A.col.s_lo, b_kstep = (int64_t)BK * p.B.row.s_lo;
+    if (p.fast) {
+        const int kbase = kt_begin * BK;
+#pragma unroll
+        for (int i = 0; i < A_CH; i++) {
+            int c = tid + i * NT;
+            int r = c / A_CPR, cp = c - r * A_CPR;
+            a_so[i] = (uint32_t)((r * L::A_LD + 2 * cp) * 8);
+            int klocal = A_MC ? r : 2 * cp;
+            a_gp[i] = Ab + a_fix[i] + (int64_t)(kbase + klocal) * p.A.col.s_lo;
+            a_nb[i] = (c < A_ROWS * A_CPR) ? (A_MC ? a_ok[i] * 8 : (a_ok[i] ? 16 : 0)) : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; i++) {
+            int c = tid + i * NT;
+            int r = c / B_CPR, cp = c - r * B_CPR;
+            b_so[i] = (uint32_t)((r * L::B_LD + 2 * cp) * 8);
+            int klocal = B_KC ? 2 * cp : r;
+            b_gp[i] = Bb + b_fix[i] + (int64_t)(kbase + klocal) * p.B.row.s_lo;
+            b_nb[i] = (c < B_ROWS * B_CPR) ? (B_KC ? (b_ok[i] ? 16 : 0) : b_ok[i] * 8) : -1;
+        }
+    }
+    const uint32_t smem_base = smem_u32(smem);
+    auto load_tile_fast = [&](int stage, int t_rel) {
+        const uint32_t sA = smem_base + (uint32_t)(stage * L::STAGE_ELEMS * 8);
+        const uint32_t sB = sA + (uint32_t)(L::A_ELEMS * 8);
+        const int64_t ao = (int64_t)t_rel * a_kstep, bo = (int64_t)t_rel * b_kstep;
+#pragma unroll
+        for (int i = 0; i < A_CH; i++) {
+            if (a_nb[i] < 0) continue;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sA + a_so[i]), "l"(a_gp[i] + ao), "r"(a_nb[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; i++) {
+            if (b_nb[i] < 0) continue;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sB + b_so[i]), "l"(b_gp[i] + bo), "r"(b_nb[i]));
+        }
+    };
+    // a tile is "full" when it lies entirely inside [0, K): no k predication needed
+    const int full_tiles_end = p.K / BK;   // tiles with index < full_tiles_end are full
+    auto load_any = [&](int stage, int t_rel) {
+        if (p.fast && (kt_begin + t_rel) < full_tiles_end) load_tile_fast(stage, t_rel);
+        else load_tile(stage, kt_begin + t_rel);
+    };
+
     double acc[MT][NTL][2];
 #pragma unroll
     for (int i = 0; i < MT; i++)
@@ -196,7 +251,7 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
     // ---- pipeline prologue -----------------------------------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nkt) load_tile(s, kt_begin + s);
+        if (s < nkt) load_any(s, s);
         cp_async_commit();
     }
 
@@ -206,7 +261,7 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
         __syncthreads();
         {
             int nxt = it + STAGES - 1;
-            if (nxt < nkt) load_tile(nxt % STAGES, kt_begin + nxt);
+            if (nxt < nkt) load_any(nxt % STAGES, nxt);
             cp_async_commit();
         }
         const double* As = smem + (size_t)(it % STAGES) * L::STAGE_ELEMS;
@@ -299,7 +354,7 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int M, int N
 namespace {
 
 struct Plan {
-    int tile;        // 1: 128x128, 2: 128x88, 3: 64x64
+    int tile;        // 1: 128x128 (16 warps), 2: 128x88, 3: 64x64, 4: 128x128 (8 warps, 32x64 warp tiles)
     int bm, bn;
     int splitk;
     bool a_mc, b_kc;
@@ -335,12 +390,13 @@ Plan make_plan(const GemmDesc& d) {
         if (splitk > 1) t += 3.0 * (double)d.M * d.N * d.batch * splitk / sms * 2.0;   // partial write + reduce traffic
         return t;
     };
-    int tiles_opt[3][2] = {{128, 128}, {128, 88}, {64, 64}};
+    int tiles_opt[4][2] = {{128, 128}, {128, 88}, {64, 64}, {128, 128}};
     double best = 1e300;
     pl.tile = 1; pl.bm = 128; pl.bn = 128; pl.splitk = 1;
     const int kt_total = (d.K + BK - 1) / BK;
-    for (int t = 0; t < 3; t++) {
+    for (int t = 0; t < 4; t++) {
         if (d.force_tile && d.force_tile != t + 1) continue;
+        if (!d.force_tile && t == 3) continue;   // tile 4 only on request until measured
         int bm = tiles_opt[t][0], bn = tiles_opt[t][1];
         for (int s = 1; s <= 64; s++) {
             if (d.force_splitk && s != d.force_splitk) continue;
@@ -403,6 +459,7 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     kp.A = d.A; kp.B = d.B; kp.C = d.C; kp.cm = d.cm; kp.cn = d.cn; kp.cb = d.cb;
     kp.alpha = d.alpha; kp.beta = d.beta;
     kp.a_vec = pl.a_vec; kp.b_vec = pl.b_vec;
+    kp.fast = (pl.a_vec && pl.b_vec && d.A.col.div == 0 && d.B.row.div == 0) ? 1 : 0;
     kp.ws = nullptr;
     if (pl.splitk > 1) {
         size_t need = (size_t)d.M * d.N * d.batch * pl.splitk * sizeof(double);
@@ -415,6 +472,7 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     int st;
     if (pl.tile == 1) st = launch_orient<128, 128, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     else if (pl.tile == 2) st = launch_orient<128, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
+    else if (pl.tile == 4) st = launch_orient<128, 128, 32, 64>(kp, pl.a_mc, pl.b_kc, stream);
     else st = launch_orient<64, 64, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     if (st) return st;
     if (pl.splitk > 1) {

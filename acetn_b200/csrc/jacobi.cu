@@ -14,80 +14,138 @@ namespace cg = cooperative_groups;
 
 namespace ab200 {
 
-constexpr int JC_WARPS = 4;   // warps per CTA
+constexpr int JB_THREADS = 512;   // 16 warps: one warp per row pair of a local step
 
 struct JacobiParams {
-    double* X;      // n x n (padded even), row major, ld = n
-    double* J;      // n x n
-    int n;
+    double* X;      // n x ld, row major (n = nb * br rows, zero padded)
+    double* J;      // n x ld
+    int n, ld, ncols;
+    int br;         // rows per block (16, or 8 for wide cores)
+    int nb;         // number of row blocks (even)
     int max_sweeps;
     double tol;
     double* conv;   // [max_sweeps] max relative off-diagonal seen in each sweep
     int* info;      // [0] sweeps used
 };
 
-__global__ void __launch_bounds__(JC_WARPS * 32) jacobi_rows_kernel(JacobiParams p) {
+// Rotate rows (xa, xb) of X (and ja, jb of J) held in shared memory so that xa . xb = 0.  One warp.
+__device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja, double* jb, int ncols, double tol, int lane) {
+    double saa = 0.0, sbb = 0.0, sab = 0.0;
+    for (int c = lane; c < ncols; c += 32) {
+        double u = xa[c], v = xb[c];
+        saa += u * u; sbb += v * v; sab += u * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        saa += __shfl_xor_sync(0xffffffffu, saa, o);
+        sbb += __shfl_xor_sync(0xffffffffu, sbb, o);
+        sab += __shfl_xor_sync(0xffffffffu, sab, o);
+    }
+    if (saa == 0.0 || sbb == 0.0) return 0.0;
+    double rel = fabs(sab) / sqrt(saa * sbb);
+    if (rel <= tol) return rel;
+    double zeta = (sbb - saa) / (2.0 * sab);
+    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+    for (int c = lane; c < ncols; c += 32) {
+        double u = xa[c], v = xb[c];
+        xa[c] = cs * u - sn * v;
+        xb[c] = sn * u + cs * v;
+        double ju = ja[c], jv = jb[c];
+        ja[c] = cs * ju - sn * jv;
+        jb[c] = sn * ju + cs * jv;
+    }
+    return rel;
+}
+
+// Block one-sided Jacobi.  Rows are grouped in nb blocks of br rows.  A sweep = one "diagonal" phase (all pairs inside
+// each block) + nb-1 round-robin phases in which every CTA owns one block pair (A,B), stages its 2*br rows of X and J
+// in shared memory and orthogonalises all br*br cross pairs in br conflict-free local steps.  Phases are separated by
+// a cooperative grid barrier (nb per sweep instead of n-1 for the plain cyclic ordering).
+__global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParams p) {
     cg::grid_group grid = cg::this_grid();
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * JC_WARPS + (threadIdx.x >> 5);
-    const int nw = gridDim.x * JC_WARPS;
-    const int n = p.n, half = n / 2, nm1 = n - 1;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int br = p.br, nb = p.nb, ld = p.ld, ncols = p.ncols;
+    const int npairs = nb / 2, nbm1 = nb - 1;
+    double* Xs = sm;                       // [2*br][ld]
+    double* Js = sm + (size_t)2 * br * ld;
 
     int sweep = 0;
     for (; sweep < p.max_sweeps; sweep++) {
         double worst = 0.0;
-        for (int step = 0; step < nm1; step++) {
-            for (int i = gw; i < half; i += nw) {
-                int a, b;
-                if (i == 0) { a = nm1; b = step; }
-                else { a = (step + i) % nm1; b = (step - i + nm1) % nm1; }
-                double* xp = p.X + (size_t)a * n;
-                double* xq = p.X + (size_t)b * n;
-                double saa = 0.0, sbb = 0.0, sab = 0.0;
-                for (int c = lane; c < n; c += 32) {
-                    double u = __ldcg(xp + c), v = __ldcg(xq + c);
-                    saa += u * u; sbb += v * v; sab += u * v;
+        for (int phase = 0; phase < nb; phase++) {
+            for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+                int A, B;
+                if (phase == 0) { A = 2 * pi; B = 2 * pi + 1; }
+                else {
+                    int s = phase - 1;
+                    if (pi == 0) { A = nbm1; B = s; }
+                    else { A = (s + pi) % nbm1; B = (s - pi + nbm1) % nbm1; }
                 }
-                saa = warp_sum(saa); sbb = warp_sum(sbb); sab = warp_sum(sab);
-                if (saa == 0.0 || sbb == 0.0) continue;
-                double rel = fabs(sab) / sqrt(saa * sbb);
-                worst = fmax(worst, rel);
-                if (rel <= p.tol) continue;
-                double zeta = (sbb - saa) / (2.0 * sab);
-                double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                double* jp = p.J + (size_t)a * n;
-                double* jq = p.J + (size_t)b * n;
-                for (int c = lane; c < n; c += 32) {
-                    double u = __ldcg(xp + c), v = __ldcg(xq + c);
-                    xp[c] = cs * u - sn * v;
-                    xq[c] = sn * u + cs * v;
-                    double ju = __ldcg(jp + c), jv = __ldcg(jq + c);
-                    jp[c] = cs * ju - sn * jv;
-                    jq[c] = sn * ju + cs * jv;
+                // stage rows of blocks A and B
+                const int rowlen2 = ld / 2;
+                for (int idx = threadIdx.x; idx < 2 * br * rowlen2; idx += JB_THREADS) {
+                    int r = idx / rowlen2, c2 = idx - r * rowlen2;
+                    int g = (r < br ? A * br + r : B * br + (r - br));
+                    reinterpret_cast<double2*>(Xs + (size_t)r * ld)[c2] = __ldcg(reinterpret_cast<const double2*>(p.X + (size_t)g * ld) + c2);
+                    reinterpret_cast<double2*>(Js + (size_t)r * ld)[c2] = __ldcg(reinterpret_cast<const double2*>(p.J + (size_t)g * ld) + c2);
                 }
+                __syncthreads();
+                if (phase == 0) {
+                    // all pairs inside A (warps [0, br/2)) and inside B (warps [br/2, br)): cyclic ordering on br players
+                    const int hb = br / 2, brm1 = br - 1;
+                    for (int t = 0; t < brm1; t++) {
+                        if (warp < br) {
+                            int blk = warp / hb, i = warp - blk * hb;
+                            int a, b;
+                            if (i == 0) { a = brm1; b = t; }
+                            else { a = (t + i) % brm1; b = (t - i + brm1) % brm1; }
+                            a += blk * br; b += blk * br;
+                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols, p.tol, lane);
+                            worst = fmax(worst, rel);
+                        }
+                        __syncthreads();
+                    }
+                } else {
+                    for (int t = 0; t < br; t++) {
+                        if (warp < br) {
+                            int a = warp, b = br + (warp + t) % br;
+                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols, p.tol, lane);
+                            worst = fmax(worst, rel);
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int idx = threadIdx.x; idx < 2 * br * rowlen2; idx += JB_THREADS) {
+                    int r = idx / rowlen2, c2 = idx - r * rowlen2;
+                    int g = (r < br ? A * br + r : B * br + (r - br));
+                    reinterpret_cast<double2*>(p.X + (size_t)g * ld)[c2] = reinterpret_cast<const double2*>(Xs + (size_t)r * ld)[c2];
+                    reinterpret_cast<double2*>(p.J + (size_t)g * ld)[c2] = reinterpret_cast<const double2*>(Js + (size_t)r * ld)[c2];
+                }
+                __syncthreads();
             }
             grid.sync();
         }
         if (lane == 0 && worst > 0.0) atomic_max_nonneg(p.conv + sweep, worst);
         grid.sync();
-        double w = *((volatile double*)(p.conv + sweep));
-        if (w <= p.tol) { sweep++; break; }
+        double wv = *((volatile double*)(p.conv + sweep));
+        if (wv <= p.tol) { sweep++; break; }
     }
-    if (gw == 0 && lane == 0) p.info[0] = sweep;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.info[0] = sweep;
 }
 
-__global__ void jacobi_init_kernel(double* X, double* J, const double* R, int q, int n) {
-    size_t total = (size_t)n * n;
+__global__ void jacobi_init_kernel(double* X, double* J, const double* R, int q, int n, int ld) {
+    size_t total = (size_t)n * ld;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int r = (int)(i / n), c = (int)(i - (size_t)r * n);
+        int r = (int)(i / ld), c = (int)(i - (size_t)r * ld);
         X[i] = (r < q && c < q) ? R[(size_t)r * q + c] : 0.0;
-        J[i] = (r == c) ? 1.0 : 0.0;
+        J[i] = (r == c && r < q) ? 1.0 : 0.0;
     }
 }
 
 // singular values = row norms; sort descending (rank by counting, stable); emit normalised rows.
-__global__ void jacobi_finalize_kernel(const double* __restrict__ X, const double* __restrict__ J, int q, int n,
+__global__ void jacobi_finalize_kernel(const double* __restrict__ X, const double* __restrict__ J, int q, int n, int ld,
                                        double* __restrict__ S, double* __restrict__ Wt, double* __restrict__ Jt, int chi,
                                        double cutoff, int* __restrict__ count, const int* __restrict__ info,
                                        double* __restrict__ sig /*[n] scratch*/, int* __restrict__ rank /*[n] scratch*/,
@@ -98,7 +156,7 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ X, const doubl
     if (phase == 0) {
         for (int r = gw; r < n; r += nw) {
             double s = 0.0;
-            for (int c = lane; c < n; c += 32) { double v = X[(size_t)r * n + c]; s += v * v; }
+            for (int c = lane; c < q; c += 32) { double v = X[(size_t)r * ld + c]; s += v * v; }
             s = warp_sum(s);
             if (lane == 0) sig[r] = sqrt(s);
         }
@@ -117,8 +175,8 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ X, const doubl
             double sr = sig[r];
             double inv = sr > 0.0 ? 1.0 / sr : 0.0;
             for (int c = lane; c < q; c += 32) {
-                Wt[(size_t)k * q + c] = X[(size_t)r * n + c] * inv;
-                Jt[(size_t)k * q + c] = J[(size_t)r * n + c];
+                Wt[(size_t)k * q + c] = X[(size_t)r * ld + c] * inv;
+                Jt[(size_t)k * q + c] = J[(size_t)r * ld + c];
             }
         }
     } else {
@@ -132,45 +190,63 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ X, const doubl
     }
 }
 
+namespace {
+struct JacobiGeom { int br, nb, n, ld; size_t smem; };
+JacobiGeom jacobi_geom(int q) {
+    JacobiGeom g;
+    g.ld = q + (q & 1);                                  // even row pitch: 16-byte staging copies
+    g.br = 16;
+    while (g.br > 2 && (size_t)4 * g.br * g.ld * sizeof(double) > 220 * 1024) g.br /= 2;
+    g.nb = (q + g.br - 1) / g.br;
+    if (g.nb & 1) g.nb++;
+    if (g.nb < 2) g.nb = 2;
+    g.n = g.nb * g.br;
+    g.smem = (size_t)4 * g.br * g.ld * sizeof(double);
+    return g;
+}
+}  // namespace
+
 size_t jacobi_workspace_bytes(int q) {
-    int n = q + (q & 1);
-    return ws_round((size_t)n * n * sizeof(double)) * 2 + ws_round(64 * sizeof(double)) + ws_round((size_t)n * sizeof(double)) +
-           ws_round((size_t)n * sizeof(int)) + ws_round(16 * sizeof(int)) + 1024;
+    JacobiGeom g = jacobi_geom(q);
+    return ws_round((size_t)g.n * g.ld * sizeof(double)) * 2 + ws_round(64 * sizeof(double)) + ws_round((size_t)g.n * sizeof(double)) +
+           ws_round((size_t)g.n * sizeof(int)) + ws_round(16 * sizeof(int)) + 1024;
 }
 
 int jacobi_svd_launch(const double* R, int q, double* S, double* Wt, double* Jt, int chi, double cutoff, int* count,
                       void* wsp, size_t ws_bytes, cudaStream_t s) {
-    AB_REQUIRE(q >= 1 && q <= 4096, "jacobi_svd: q=%d out of range", q);
-    const int n = q + (q & 1);
+    AB_REQUIRE(q >= 1 && q <= 3400, "jacobi_svd: q=%d out of range (1..3400)", q);
+    const JacobiGeom g = jacobi_geom(q);
     const int max_sweeps = 60;
     Workspace ws(wsp, ws_bytes);
-    double* X = ws.take<double>((size_t)n * n);
-    double* J = ws.take<double>((size_t)n * n);
+    double* X = ws.take<double>((size_t)g.n * g.ld);
+    double* J = ws.take<double>((size_t)g.n * g.ld);
     double* conv = ws.take<double>(64);
-    double* sig = ws.take<double>(n);
-    int* rank = ws.take<int>(n);
+    double* sig = ws.take<double>(g.n);
+    int* rank = ws.take<int>(g.n);
     int* info = ws.take<int>(16);
     if (ws.overflow) { set_error("jacobi_svd: workspace too small"); return ERR_WORKSPACE; }
     AB_CHECK_CUDA(cudaMemsetAsync(conv, 0, 64 * sizeof(double), s));
     AB_CHECK_CUDA(cudaMemsetAsync(info, 0, 16 * sizeof(int), s));
-    jacobi_init_kernel<<<148, 256, 0, s>>>(X, J, R, q, n);
+    jacobi_init_kernel<<<148, 256, 0, s>>>(X, J, R, q, g.n, g.ld);
     AB_LAUNCHED();
-    if (n >= 2) {
+    {
+        static size_t configured = 0;
+        if (g.smem > configured) {
+            AB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            configured = g.smem;
+        }
         JacobiParams p;
-        p.X = X; p.J = J; p.n = n; p.max_sweeps = max_sweeps; p.tol = 2.3e-16 * sqrt((double)(n > 64 ? n : 64)); p.conv = conv; p.info = info;
-        int half = n / 2;
-        int blocks = (half + JC_WARPS - 1) / JC_WARPS;
-        int maxb = 0;
-        AB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb, jacobi_rows_kernel, JC_WARPS * 32, 0));
-        int cap = maxb * device_sm_count();
-        if (cap < 1) cap = 1;
+        p.X = X; p.J = J; p.n = g.n; p.ld = g.ld; p.ncols = q; p.br = g.br; p.nb = g.nb; p.max_sweeps = max_sweeps;
+        p.tol = 2.3e-16 * sqrt((double)(q > 64 ? q : 64)); p.conv = conv; p.info = info;
+        int blocks = g.nb / 2;
+        int cap = device_sm_count();
         if (blocks > cap) blocks = cap;
         void* args[] = {&p};
-        AB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_rows_kernel, dim3(blocks), dim3(JC_WARPS * 32), args, 0, s));
+        AB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel, dim3(blocks), dim3(JB_THREADS), args, g.smem, s));
         note_launch(1);
     }
     for (int phase = 0; phase < 4; phase++) {
-        jacobi_finalize_kernel<<<phase == 3 ? 1 : 64, 256, 0, s>>>(X, J, q, n, S, Wt, Jt, chi, cutoff, count, info, sig, rank, phase);
+        jacobi_finalize_kernel<<<phase == 3 ? 1 : 64, 256, 0, s>>>(X, J, q, g.n, g.ld, S, Wt, Jt, chi, cutoff, count, info, sig, rank, phase);
         AB_LAUNCHED();
     }
     return OK;

@@ -16,32 +16,48 @@ constexpr int TS_CH = 256;   // rows per chunk (one thread per row)
 constexpr int TS_PB = 32;    // panel width
 constexpr int TS_NW = TS_CH / 32;
 
+// Thread layout of both kernels: lane = column of the panel (b <= 32), warp w owns rows [32w, 32w+32) of the chunk;
+// every thread keeps its 32 rows of its column in registers, so a Householder step is 32 FMAs for the dot, an 8-way
+// partial sum through shared memory and 32 FMAs for the update -- no warp shuffles on the critical path.
+
 // Factor one chunk: P[r0:r0+rows, 0:b] = H_0 ... H_{b-1} [R; 0].  Reflectors overwrite the strictly lower part of P.
 __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
                    double* __restrict__ tau_out) {
-    extern __shared__ double sm[];
-    double* S = sm;                       // column major: S[c*TS_CH + r]
-    double* tau_s = sm + TS_PB * TS_CH;   // [TS_PB]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double v_s[TS_CH];            // current reflector (0 above its diagonal, 1 on it)
+    __shared__ double part[TS_NW][TS_PB];    // per-warp partial dots
+    __shared__ double partn[TS_NW];          // per-warp partial norms of the pivot column
+    __shared__ double alpha_s;
+    __shared__ double tau_s[TS_PB];
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
     const int nref = b < rows ? b : rows;
+    const int rbase = 32 * w;
 
-    for (int idx = tid; idx < rows * b; idx += TS_CH) {
-        int r = idx / b, c = idx - r * b;
-        S[c * TS_CH + r] = P[(r0 + r) * ld + c];
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int r = rbase + i;
+        x[i] = (r < rows && c < b) ? P[(r0 + r) * ld + c] : 0.0;
     }
     if (tid < TS_PB) tau_s[tid] = 0.0;
-    __syncthreads();
 
-    // builds the reflector of column c from rows >= c (one full warp)
-    auto prepare = [&](int c) {
-        double* col = S + c * TS_CH;
+    for (int j = 0; j < nref; j++) {
+        // ---- reflector j from column j, rows >= j
+        if (c == j) {
+            double pn = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i++) pn += (rbase + i > j) ? x[i] * x[i] : 0.0;
+            partn[w] = pn;
+#pragma unroll
+            for (int i = 0; i < 32; i++) if (rbase + i == j) alpha_s = x[i];
+        }
+        __syncthreads();
         double ss = 0.0;
-        for (int r = c + 1 + lane; r < rows; r += 32) ss += col[r] * col[r];
-        ss = warp_sum(ss);
-        double alpha = col[c];
+#pragma unroll
+        for (int k = 0; k < TS_NW; k++) ss += partn[k];
+        const double alpha = alpha_s;
         double tau = 0.0, beta = alpha, scale = 0.0;
         if (ss != 0.0) {
             double nrm = sqrt(alpha * alpha + ss);
@@ -49,37 +65,39 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             tau = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
-        for (int r = c + 1 + lane; r < rows; r += 32) col[r] *= scale;
-        __syncwarp();
-        if (lane == 0) { col[c] = beta; tau_s[c] = tau; }
-    };
-
-    if (warp == 0 && nref > 0) prepare(0);
-    __syncthreads();
-    for (int j = 0; j < nref; j++) {
-        const double tau = tau_s[j];
-        const double* vcol = S + j * TS_CH;
-        for (int c = j + 1 + warp; c < b; c += TS_NW) {
-            double* col = S + c * TS_CH;
-            double dot = 0.0;
-            for (int r = j + 1 + lane; r < rows; r += 32) dot += vcol[r] * col[r];
-            dot = (warp_sum(dot) + col[j]) * tau;
-            __syncwarp();
-            for (int r = j + 1 + lane; r < rows; r += 32) col[r] -= vcol[r] * dot;
-            if (lane == 0) col[j] -= dot;
-            __syncwarp();
-            if (c == j + 1 && c < nref) prepare(c);
+        if (c == j) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                int r = rbase + i;
+                if (r > j) { x[i] *= scale; v_s[r] = x[i]; }
+                else if (r == j) { x[i] = beta; v_s[r] = 1.0; }
+                else v_s[r] = 0.0;
+            }
+            if (w == 0) tau_s[j] = tau;
         }
         __syncthreads();
+        // ---- apply H_j to the trailing columns
+        double dsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) dsum += v_s[rbase + i] * x[i];
+        part[w][c] = dsum;
+        __syncthreads();
+        if (c > j && c < b) {
+            double wc = 0.0;
+#pragma unroll
+            for (int k = 0; k < TS_NW; k++) wc += part[k][c];
+            wc *= tau;
+#pragma unroll
+            for (int i = 0; i < 32; i++) x[i] -= v_s[rbase + i] * wc;
+        }
     }
+    __syncthreads();
     // reflectors (and R) back to P; R block (b x b, zero below the diagonal / beyond rows) to the stack
-    for (int idx = tid; idx < rows * b; idx += TS_CH) {
-        int r = idx / b, c = idx - r * b;
-        P[(r0 + r) * ld + c] = S[c * TS_CH + r];
-    }
-    for (int idx = tid; idx < b * b; idx += TS_CH) {
-        int i = idx / b, c = idx - i * b;
-        Rstack[((int64_t)blockIdx.x * b + i) * b + c] = (i <= c && i < nref) ? S[c * TS_CH + i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int r = rbase + i;
+        if (r < rows && c < b) P[(r0 + r) * ld + c] = x[i];
+        if (r < b && c < b) Rstack[((int64_t)blockIdx.x * b + r) * b + c] = (r <= c && r < nref) ? x[i] : 0.0;
     }
     if (tid < b) tau_out[(int64_t)blockIdx.x * b + tid] = tau_s[tid];
 }
@@ -89,50 +107,56 @@ __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
                   const double* __restrict__ Min) {
     extern __shared__ double sm[];
-    double* S = sm;                        // reflectors, column major
-    double* Z = sm + TS_PB * TS_CH;        // result, column major
-    double* tau_s = Z + TS_PB * TS_CH;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int VP = TS_CH + 1;                  // odd pitch: conflict-free column-strided stores
+    double* Vs = sm;                               // [TS_PB][VP]: reflector j with unit diagonal, zeros above
+    double* part = sm + TS_PB * VP;             // [2][TS_NW][TS_PB]
+    double* tau_s = part + 2 * TS_NW * TS_PB;      // [TS_PB]
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
     const int nref = b < rows ? b : rows;
+    const int rbase = 32 * w;
 
-    for (int idx = tid; idx < rows * b; idx += TS_CH) {
-        int r = idx / b, c = idx - r * b;
-        S[c * TS_CH + r] = P[(r0 + r) * ld + c];
-        double z = 0.0;
-        if (r < nref) z = Min ? Min[((int64_t)blockIdx.x * b + r) * b + c] : (r == c ? 1.0 : 0.0);
-        Z[c * TS_CH + r] = z;
+    double z[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int r = rbase + i;
+        double v = (r < rows && c < b) ? P[(r0 + r) * ld + c] : 0.0;
+        Vs[c * VP + r] = (r > c) ? v : (r == c ? 1.0 : 0.0);
+        double zz = 0.0;
+        if (r < nref && c < b) zz = Min ? Min[((int64_t)blockIdx.x * b + r) * b + c] : (r == c ? 1.0 : 0.0);
+        z[i] = zz;
     }
     if (tid < TS_PB) tau_s[tid] = tid < b ? tau_in[(int64_t)blockIdx.x * b + tid] : 0.0;
     __syncthreads();
 
-    // each warp owns columns c = warp, warp+8, ... of Z; no cross-warp dependency
+    int buf = 0;
     for (int j = nref - 1; j >= 0; j--) {
-        const double tau = tau_s[j];
-        if (tau == 0.0) continue;
-        const double* vcol = S + j * TS_CH;
-        for (int c = warp; c < b; c += TS_NW) {
-            double* zc = Z + c * TS_CH;
-            double dot = 0.0;
-            for (int r = j + 1 + lane; r < rows; r += 32) dot += vcol[r] * zc[r];
-            dot = (warp_sum(dot) + zc[j]) * tau;
-            __syncwarp();
-            for (int r = j + 1 + lane; r < rows; r += 32) zc[r] -= vcol[r] * dot;
-            if (lane == 0) zc[j] -= dot;
-            __syncwarp();
-        }
+        const double* v = Vs + j * VP + rbase;
+        double dsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) dsum += v[i] * z[i];
+        double* pb = part + buf * TS_NW * TS_PB;
+        pb[w * TS_PB + c] = dsum;
+        __syncthreads();
+        double wc = 0.0;
+#pragma unroll
+        for (int k = 0; k < TS_NW; k++) wc += pb[k * TS_PB + c];
+        wc *= tau_s[j];
+#pragma unroll
+        for (int i = 0; i < 32; i++) z[i] -= v[i] * wc;
+        buf ^= 1;
     }
-    __syncthreads();
-    for (int idx = tid; idx < rows * b; idx += TS_CH) {
-        int r = idx / b, c = idx - r * b;
-        P[(r0 + r) * ld + c] = Z[c * TS_CH + r];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int r = rbase + i;
+        if (r < rows && c < b) P[(r0 + r) * ld + c] = z[i];
     }
 }
 
 namespace {
-constexpr size_t FACTOR_SMEM = (size_t)(TS_PB * TS_CH + TS_PB) * sizeof(double);
-constexpr size_t APPLY_SMEM = (size_t)(2 * TS_PB * TS_CH + TS_PB) * sizeof(double);
+constexpr size_t FACTOR_SMEM = 0;
+constexpr size_t APPLY_SMEM = (size_t)(TS_PB * (TS_CH + 1) + 2 * TS_NW * TS_PB + TS_PB) * sizeof(double);
 
 struct Levels {
     int n;
@@ -161,7 +185,6 @@ size_t tsqr_scratch_doubles(int64_t m) {
 int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FACTOR_SMEM));
         AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
         configured = true;
     }
