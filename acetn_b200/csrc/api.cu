@@ -160,7 +160,7 @@ size_t acetn_b200_quarter_tensor_workspace_bytes(int64_t xa, int64_t xb, int64_t
 }
 int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E1, const double* A, const int64_t* a_strides,
                               int64_t xa, int64_t xb, int64_t xc, int64_t xe, int64_t D, int64_t d, int normalize, double* Q,
-                              void* wsp, size_t ws_bytes, void* stream) {
+                              double* absmax_out, void* wsp, size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     QuarterDims q{xa, xb, xc, xe, D, d};
     const int64_t D2 = D * D, N2 = xe * D2, M2 = xc * D2;
@@ -180,13 +180,13 @@ int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E
     a.order = 0; a.A = A; a.D = D; a.d = d; a.Y = Q; a.out_s0 = D2 * N2; a.out_s1 = D2;
     a.out_es[0] = D * N2; a.out_es[1] = N2; a.out_es[2] = D; a.out_es[3] = 1;
     for (int i = 0; i < 5; i++) a.a_s[i] = a_strides[i];
-    if (normalize) AB_CHECK_CUDA(cudaMemsetAsync(mx, 0, 8, s));
+    const bool want_max = normalize || absmax_out != nullptr;
+    if (absmax_out) mx = absmax_out;
+    if (want_max) AB_CHECK_CUDA(cudaMemsetAsync(mx, 0, 8, s));
     const bool fused = double_layer_fused_supported(D, d) != 0;
-    AB_TRY(double_layer(a, (normalize && fused) ? mx : nullptr, rest, rest_bytes, s));
-    if (normalize) {
-        if (!fused) AB_TRY(absmax_launch(Q, (size_t)(M2 * N2), mx, s));
-        AB_TRY(scale_inv_launch(Q, (size_t)(M2 * N2), mx, s));
-    }
+    AB_TRY(double_layer(a, (want_max && fused) ? mx : nullptr, rest, rest_bytes, s));
+    if (want_max && !fused) AB_TRY(absmax_launch(Q, (size_t)(M2 * N2), mx, s));
+    if (normalize) AB_TRY(scale_inv_launch(Q, (size_t)(M2 * N2), mx, s));
     return OK;
 }
 
@@ -324,7 +324,8 @@ size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4,
 }
 int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
                                    const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S, int64_t keep,
-                                   double* proj1, double* proj2, void* wsp, size_t ws_bytes, void* stream) {
+                                   const double* qmax1, const double* qmax4, double* proj1, double* proj2, void* wsp,
+                                   size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     AB_REQUIRE(keep >= 1, "projectors: keep must be >= 1");
     Workspace ws(wsp, ws_bytes);
@@ -335,8 +336,8 @@ int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, con
     void* g = ws.base + ws.used;
     size_t gb = ws.bytes - ws.used;
     AB_TRY(inv_sqrt_weights_launch(S, w, (int)keep, s));
-    AB_TRY(scale_cols_launch(Us, keep, U, ldu, w, m1, (int)keep, s));
-    AB_TRY(scale_cols_launch(Vs, keep, V, ldv, w, n4, (int)keep, s));
+    AB_TRY(scale_cols_launch(Us, keep, U, ldu, w, qmax1, m1, (int)keep, s));
+    AB_TRY(scale_cols_launch(Vs, keep, V, ldv, w, qmax4, n4, (int)keep, s));
     AB_TRY(gemm_launch(p1_desc(Q1, m1, n1, Us, keep, proj1), g, gb, s));
     AB_TRY(gemm_launch(p2_desc(Q4, m4, n4, Vs, keep, proj2), g, gb, s));
     return OK;

@@ -82,112 +82,81 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
     constexpr int B_ROWS = L::B_ROWS, B_COLS = B_KC ? BK : BN, B_CPR = B_COLS / 2;
     constexpr int B_CH = (B_ROWS * B_CPR + NT - 1) / NT;
 
-    int64_t a_fix[A_CH];   // offset of the m index (loop invariant); for the 2 elements of a chunk when m is contiguous
-    int a_ok[A_CH];        // number of valid elements along m in this chunk (0..2) (A_MC) or 0/1 (!A_MC)
-    int64_t a_fix1[A_CH];  // offset of the second element (scalar path, m contiguous)
-#pragma unroll
-    for (int i = 0; i < A_CH; i++) {
-        int c = tid + i * NT;
-        int r = c / A_CPR, cp = c - r * A_CPR;
-        a_fix[i] = 0; a_fix1[i] = 0; a_ok[i] = 0;
-        if (c < A_ROWS * A_CPR) {
-            if (A_MC) {
-                int m = m0 + 2 * cp;
-                if (m < p.M) { a_fix[i] = p.A.row.off(m); a_ok[i] = 1; }
-                if (m + 1 < p.M) { a_fix1[i] = p.A.row.off(m + 1); a_ok[i] = 2; }
-            } else {
-                int m = m0 + r;
-                if (m < p.M) { a_fix[i] = p.A.row.off(m); a_ok[i] = 1; }
-            }
-        }
-    }
-    int64_t b_fix[B_CH], b_fix1[B_CH];
-    int b_ok[B_CH];
-#pragma unroll
-    for (int i = 0; i < B_CH; i++) {
-        int c = tid + i * NT;
-        int r = c / B_CPR, cp = c - r * B_CPR;
-        b_fix[i] = 0; b_fix1[i] = 0; b_ok[i] = 0;
-        if (c < B_ROWS * B_CPR) {
-            if (B_KC) {
-                int n = n0 + r;
-                if (n < p.N) { b_fix[i] = p.B.col.off(n); b_ok[i] = 1; }
-            } else {
-                int n = n0 + 2 * cp;
-                if (n < p.N) { b_fix[i] = p.B.col.off(n); b_ok[i] = 1; }
-                if (n + 1 < p.N) { b_fix1[i] = p.B.col.off(n + 1); b_ok[i] = 2; }
-            }
-        }
-    }
-
+    // general (slow) loader: every address is recomputed from the two-level descriptors; used for odd shapes,
+    // non-vectorisable operands, two-level k indices and the k-remainder tile
     auto load_tile = [&](int stage, int kt) {
         double* As = smem + (size_t)stage * L::STAGE_ELEMS;
         double* Bs = As + L::A_ELEMS;
         const int k0 = kt * BK;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < A_CH; i++) {
             int c = tid + i * NT;
             if (c >= A_ROWS * A_CPR) continue;
             int r = c / A_CPR, cp = c - r * A_CPR;
             double* dst = As + r * L::A_LD + 2 * cp;
             if (A_MC) {
-                int k = k0 + r;
+                int m = m0 + 2 * cp, k = k0 + r;
                 bool kok = k < p.K;
+                int nv = kok ? (m + 1 < p.M ? 2 : (m < p.M ? 1 : 0)) : 0;
                 int64_t ko = kok ? p.A.col.off(k) : 0;
-                int nv = kok ? a_ok[i] : 0;
+                int64_t f0 = nv >= 1 ? p.A.row.off(m) : 0;
                 if (p.a_vec) {
-                    cp_async16(dst, Ab + a_fix[i] + ko, nv * 8);
+                    cp_async16(dst, Ab + f0 + ko, nv * 8);
                 } else {
-                    cp_async8(dst, Ab + a_fix[i] + ko, nv >= 1 ? 8 : 0);
-                    cp_async8(dst + 1, Ab + a_fix1[i] + ko, nv >= 2 ? 8 : 0);
+                    int64_t f1 = nv >= 2 ? p.A.row.off(m + 1) : 0;
+                    cp_async8(dst, Ab + f0 + ko, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Ab + f1 + ko, nv >= 2 ? 8 : 0);
                 }
             } else {
-                int k = k0 + 2 * cp;
-                int nv = a_ok[i] ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                int m = m0 + r, k = k0 + 2 * cp;
+                int nv = (m < p.M) ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                int64_t f0 = nv ? p.A.row.off(m) : 0;
                 if (p.a_vec) {
                     int64_t ko = nv ? p.A.col.off(k) : 0;
-                    cp_async16(dst, Ab + a_fix[i] + ko, nv * 8);
+                    cp_async16(dst, Ab + f0 + ko, nv * 8);
                 } else {
                     int64_t ko0 = nv >= 1 ? p.A.col.off(k) : 0;
                     int64_t ko1 = nv >= 2 ? p.A.col.off(k + 1) : 0;
-                    cp_async8(dst, Ab + a_fix[i] + ko0, nv >= 1 ? 8 : 0);
-                    cp_async8(dst + 1, Ab + a_fix[i] + ko1, nv >= 2 ? 8 : 0);
+                    cp_async8(dst, Ab + f0 + ko0, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Ab + f0 + ko1, nv >= 2 ? 8 : 0);
                 }
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < B_CH; i++) {
             int c = tid + i * NT;
             if (c >= B_ROWS * B_CPR) continue;
             int r = c / B_CPR, cp = c - r * B_CPR;
             double* dst = Bs + r * L::B_LD + 2 * cp;
             if (B_KC) {
-                int k = k0 + 2 * cp;
-                int nv = b_ok[i] ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                int n = n0 + r, k = k0 + 2 * cp;
+                int nv = (n < p.N) ? (k + 1 < p.K ? 2 : (k < p.K ? 1 : 0)) : 0;
+                int64_t f0 = nv ? p.B.col.off(n) : 0;
                 if (p.b_vec) {
                     int64_t ko = nv ? p.B.row.off(k) : 0;
-                    cp_async16(dst, Bb + b_fix[i] + ko, nv * 8);
+                    cp_async16(dst, Bb + f0 + ko, nv * 8);
                 } else {
                     int64_t ko0 = nv >= 1 ? p.B.row.off(k) : 0;
                     int64_t ko1 = nv >= 2 ? p.B.row.off(k + 1) : 0;
-                    cp_async8(dst, Bb + b_fix[i] + ko0, nv >= 1 ? 8 : 0);
-                    cp_async8(dst + 1, Bb + b_fix[i] + ko1, nv >= 2 ? 8 : 0);
+                    cp_async8(dst, Bb + f0 + ko0, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Bb + f0 + ko1, nv >= 2 ? 8 : 0);
                 }
             } else {
-                int k = k0 + r;
+                int n = n0 + 2 * cp, k = k0 + r;
                 bool kok = k < p.K;
+                int nv = kok ? (n + 1 < p.N ? 2 : (n < p.N ? 1 : 0)) : 0;
                 int64_t ko = kok ? p.B.row.off(k) : 0;
-                int nv = kok ? b_ok[i] : 0;
+                int64_t f0 = nv >= 1 ? p.B.col.off(n) : 0;
                 if (p.b_vec) {
-                    cp_async16(dst, Bb + b_fix[i] + ko, nv * 8);
+                    cp_async16(dst, Bb + f0 + ko, nv * 8);
                 } else {
-                    cp_async8(dst, Bb + b_fix[i] + ko, nv >= 1 ? 8 : 0);
-                    cp_async8(dst + 1, Bb + b_fix1[i] + ko, nv >= 2 ? 8 : 0);
+                    int64_t f1 = nv >= 2 ? p.B.col.off(n + 1) : 0;
+                    cp_async8(dst, Bb + f0 + ko, nv >= 1 ? 8 : 0);
+                    cp_async8(dst + 1, Bb + f1 + ko, nv >= 2 ? 8 : 0);
                 }
             }
         }
     };
-
 
     // ---- fast loader state (p.fast): one global pointer + one smem byte offset + byte count per 16-byte chunk; the k
     //      advance is a single add per tile, so the steady-state loop issues ~4 instructions per chunk ------------------
@@ -206,8 +175,11 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
             int r = c / A_CPR, cp = c - r * A_CPR;
             a_so[i] = (uint32_t)((r * L::A_LD + 2 * cp) * 8);
             int klocal = A_MC ? r : 2 * cp;
-            a_gp[i] = Ab + a_fix[i] + (int64_t)(kbase + klocal) * p.A.col.s_lo;
-            a_nb[i] = (c < A_ROWS * A_CPR) ? (A_MC ? a_ok[i] * 8 : (a_ok[i] ? 16 : 0)) : -1;
+            int m = A_MC ? m0 + 2 * cp : m0 + r;
+            int okc = A_MC ? (m + 1 < p.M ? 2 : (m < p.M ? 1 : 0)) : (m < p.M ? 1 : 0);
+            int64_t fix = okc ? p.A.row.off(m) : 0;
+            a_gp[i] = Ab + fix + (int64_t)(kbase + klocal) * p.A.col.s_lo;
+            a_nb[i] = (c < A_ROWS * A_CPR) ? (A_MC ? okc * 8 : (okc ? 16 : 0)) : -1;
         }
 #pragma unroll
         for (int i = 0; i < B_CH; i++) {
@@ -215,8 +187,11 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
             int r = c / B_CPR, cp = c - r * B_CPR;
             b_so[i] = (uint32_t)((r * L::B_LD + 2 * cp) * 8);
             int klocal = B_KC ? 2 * cp : r;
-            b_gp[i] = Bb + b_fix[i] + (int64_t)(kbase + klocal) * p.B.row.s_lo;
-            b_nb[i] = (c < B_ROWS * B_CPR) ? (B_KC ? (b_ok[i] ? 16 : 0) : b_ok[i] * 8) : -1;
+            int n = B_KC ? n0 + r : n0 + 2 * cp;
+            int okc = B_KC ? (n < p.N ? 1 : 0) : (n + 1 < p.N ? 2 : (n < p.N ? 1 : 0));
+            int64_t fix = okc ? p.B.col.off(n) : 0;
+            b_gp[i] = Bb + fix + (int64_t)(kbase + klocal) * p.B.row.s_lo;
+            b_nb[i] = (c < B_ROWS * B_CPR) ? (B_KC ? (okc ? 16 : 0) : okc * 8) : -1;
         }
     }
     const uint32_t smem_base = smem_u32(smem);
@@ -256,35 +231,70 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
     }
 
     const int lr = lane >> 2, lc = lane & 3;
+    constexpr int KSTEPS = BK / 4;
+    // per-fragment smem element offsets of this thread (stage- and k-step-independent part)
+    int a_off[MT], b_off[NTL];
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+        int m = wm0 + i * 8 + lr;
+        a_off[i] = A_MC ? (lc * L::A_LD + m) : (m * L::A_LD + lc);
+    }
+#pragma unroll
+    for (int j = 0; j < NTL; j++) {
+        int n = wn0 + j * 8 + lr;
+        b_off[j] = B_KC ? (n * L::B_LD + lc) : (lc * L::B_LD + n);
+    }
+    constexpr int A_KSTRIDE = A_MC ? 4 * L::A_LD : 4;   // smem element stride of one k-step
+    constexpr int B_KSTRIDE = B_KC ? 4 : 4 * L::B_LD;
+
     for (int it = 0; it < nkt; it++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nxt = it + STAGES - 1;
-            if (nxt < nkt) load_any(nxt % STAGES, nxt);
-            cp_async_commit();
-        }
+        const int nxt = it + STAGES - 1;
+        const bool do_load = nxt < nkt;
+        const bool fast_tile = do_load && p.fast && (kt_begin + nxt) < full_tiles_end;
+        if (do_load && !fast_tile) load_tile(nxt % STAGES, kt_begin + nxt);
+        // fast path: the 16-byte copies of the next tile are issued one by one between the DMMAs below, so the
+        // address arithmetic overlaps the tensor pipe instead of forming a loader phase after the barrier
+        const uint32_t sA_n = smem_base + (uint32_t)((nxt % STAGES) * L::STAGE_ELEMS * 8);
+        const uint32_t sB_n = sA_n + (uint32_t)(L::A_ELEMS * 8);
+        const int64_t ao = (int64_t)nxt * a_kstep, bo = (int64_t)nxt * b_kstep;
+
         const double* As = smem + (size_t)(it % STAGES) * L::STAGE_ELEMS;
         const double* Bs = As + L::A_ELEMS;
+        double af[2][MT], bf[2][NTL];
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; kk++) {
-            double af[MT], bf[NTL];
-            const int k = kk * 4 + lc;
+        for (int i = 0; i < MT; i++) af[0][i] = As[a_off[i]];
 #pragma unroll
-            for (int i = 0; i < MT; i++) {
-                int m = wm0 + i * 8 + lr;
-                af[i] = A_MC ? As[k * L::A_LD + m] : As[m * L::A_LD + k];
+        for (int j = 0; j < NTL; j++) bf[0][j] = Bs[b_off[j]];
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; kk++) {
+            const int cur = kk & 1, nx = cur ^ 1;
+            if (kk + 1 < KSTEPS) {
+#pragma unroll
+                for (int i = 0; i < MT; i++) af[nx][i] = As[a_off[i] + (kk + 1) * A_KSTRIDE];
+#pragma unroll
+                for (int j = 0; j < NTL; j++) bf[nx][j] = Bs[b_off[j] + (kk + 1) * B_KSTRIDE];
             }
 #pragma unroll
             for (int j = 0; j < NTL; j++) {
-                int n = wn0 + j * 8 + lr;
-                bf[j] = B_KC ? Bs[n * L::B_LD + k] : Bs[k * L::B_LD + n];
+#pragma unroll
+                for (int i = 0; i < MT; i++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+                // one copy chunk per n-tile slot, starting with the second k-step
+                if (kk >= 1) {
+                    const int slot = (kk - 1) * NTL + j;
+                    if (slot < A_CH) {
+                        if (fast_tile && a_nb[slot] >= 0)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sA_n + a_so[slot]), "l"(a_gp[slot] + ao), "r"(a_nb[slot]));
+                    } else if (slot < A_CH + B_CH) {
+                        if (fast_tile && b_nb[slot - A_CH] >= 0)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sB_n + b_so[slot - A_CH]), "l"(b_gp[slot - A_CH] + bo), "r"(b_nb[slot - A_CH]));
+                    }
+                }
             }
-#pragma unroll
-            for (int i = 0; i < MT; i++)
-#pragma unroll
-                for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        static_assert(A_CH + B_CH <= (KSTEPS - 1) * NTL, "not enough DMMA slots to interleave the tile copies");
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -341,8 +351,13 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int M, int N
         size_t r = idx - (size_t)b * mn;
         int m = (int)(r / N), n = (int)(r - (size_t)m * N);
         const double* w = ws + (size_t)b * splitk * mn + r;
-        double s = 0.0;
-        for (int z = 0; z < splitk; z++) s += w[(size_t)z * mn];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int z = 0;
+        for (; z + 3 < splitk; z += 4) {   // fixed summation order => deterministic; 4 loads in flight
+            s0 += w[(size_t)z * mn]; s1 += w[(size_t)(z + 1) * mn]; s2 += w[(size_t)(z + 2) * mn]; s3 += w[(size_t)(z + 3) * mn];
+        }
+        for (; z < splitk; z++) s0 += w[(size_t)z * mn];
+        double s = (s0 + s1) + (s2 + s3);
         double* dst = C + cb.off(b) + cm.off(m) + cn.off(n);
         double v = alpha * s;
         if (beta != 0.0) v += beta * (*dst);
@@ -354,7 +369,7 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int M, int N
 namespace {
 
 struct Plan {
-    int tile;        // 1: 128x128 (16 warps), 2: 128x88, 3: 64x64, 4: 128x128 (8 warps, 32x64 warp tiles)
+    int tile;        // 1: 128x128 (16 warps), 2: 128x88, 3: 64x64, 4: 128x128 (8 warps, 32x64 warp tiles), 5: 64x88 (4 warps)
     int bm, bn;
     int splitk;
     bool a_mc, b_kc;
@@ -390,19 +405,19 @@ Plan make_plan(const GemmDesc& d) {
         if (splitk > 1) t += 3.0 * (double)d.M * d.N * d.batch * splitk / sms * 2.0;   // partial write + reduce traffic
         return t;
     };
-    int tiles_opt[4][2] = {{128, 128}, {128, 88}, {64, 64}, {128, 128}};
+    int tiles_opt[5][2] = {{128, 128}, {128, 88}, {64, 64}, {128, 128}, {64, 88}};
     double best = 1e300;
     pl.tile = 1; pl.bm = 128; pl.bn = 128; pl.splitk = 1;
     const int kt_total = (d.K + BK - 1) / BK;
-    for (int t = 0; t < 4; t++) {
+    for (int t = 0; t < 5; t++) {
         if (d.force_tile && d.force_tile != t + 1) continue;
-        if (!d.force_tile && t == 3) continue;   // tile 4 only on request until measured
+        if (!d.force_tile && t >= 3) continue;   // tiles 4,5 only on request until measured
         int bm = tiles_opt[t][0], bn = tiles_opt[t][1];
         for (int s = 1; s <= 64; s++) {
             if (d.force_splitk && s != d.force_splitk) continue;
             if (s > 1 && kt_total / s < 8) break;
             double c = waves_cost(bm, bn, s);
-            if (t == 2) c *= 1.25;   // 64x64 tiles run at lower efficiency per flop
+            if (t == 0) c *= 1.15;   // measured: 128x128 (16 warps, 128 regs) 28 TF vs 64x64 (3 CTAs/SM) 32 TF on square shapes
             if (c < best) { best = c; pl.tile = t + 1; pl.bm = bm; pl.bn = bn; pl.splitk = s; }
         }
     }
@@ -473,6 +488,7 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     if (pl.tile == 1) st = launch_orient<128, 128, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     else if (pl.tile == 2) st = launch_orient<128, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
     else if (pl.tile == 4) st = launch_orient<128, 128, 32, 64>(kp, pl.a_mc, pl.b_kc, stream);
+    else if (pl.tile == 5) st = launch_orient<64, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
     else st = launch_orient<64, 64, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     if (st) return st;
     if (pl.splitk > 1) {

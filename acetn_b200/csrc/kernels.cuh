@@ -15,9 +15,9 @@ size_t frob_scratch_doubles();
 int frob_normalize_launch(double* x, size_t n, double* scratch, cudaStream_t s);
 // dst (contiguous, dims d0..d4 row-major) = src[i0*s0 + ... + i4*s4]
 int gather5_launch(double* dst, const double* src, const int64_t dims[5], const int64_t strides[5], cudaStream_t s);
-// dst[r*ldd + c] = src[r*lds + c] * w[c]   for c < ncols
-int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, int64_t nrows,
-                      int ncols, cudaStream_t s);
+// dst[r*ldd + c] = src[r*lds + c] * w[c] / *div   for c < ncols   (w, div optional)
+int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, const double* div,
+                      int64_t nrows, int ncols, cudaStream_t s);
 int copy2d_launch(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t nrows, int ncols, cudaStream_t s);
 // sum_i a[i]*b[i] (deterministic) -> *dst ; scratch as frob
 int dot_launch(const double* a, const double* b, size_t n, double* dst, double* scratch, cudaStream_t s);

@@ -117,13 +117,15 @@ __global__ void gather5_kernel(double* __restrict__ dst, const double* __restric
 }
 
 __global__ void scale_cols_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
-                                  const double* __restrict__ w, int64_t nrows, int ncols) {
+                                  const double* __restrict__ w, const double* __restrict__ div, int64_t nrows, int ncols) {
     size_t total = (size_t)nrows * ncols;
+    double g = 1.0;
+    if (div) { double dv = *div; g = dv != 0.0 ? 1.0 / dv : 1.0; }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int64_t r = i / ncols;
         int c = (int)(i - r * ncols);
         double v = src[r * lds + c];
-        dst[r * ldd + c] = w ? v * w[c] : v;
+        dst[r * ldd + c] = (w ? v * w[c] : v) * g;
     }
 }
 
@@ -176,16 +178,16 @@ int gather5_launch(double* dst, const double* src, const int64_t dims[5], const 
     AB_LAUNCHED();
     return OK;
 }
-int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, int64_t nrows, int ncols,
-                      cudaStream_t s) {
+int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, const double* div, int64_t nrows,
+                      int ncols, cudaStream_t s) {
     size_t total = (size_t)nrows * ncols;
     if (total == 0) return OK;
-    scale_cols_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, ldd, src, lds, w, nrows, ncols);
+    scale_cols_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, ldd, src, lds, w, div, nrows, ncols);
     AB_LAUNCHED();
     return OK;
 }
 int copy2d_launch(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t nrows, int ncols, cudaStream_t s) {
-    return scale_cols_launch(dst, ldd, src, lds, nullptr, nrows, ncols, s);
+    return scale_cols_launch(dst, ldd, src, lds, nullptr, nullptr, nrows, ncols, s);
 }
 int inv_sqrt_weights_launch(const double* S, double* w, int ncols, cudaStream_t s) {
     if (ncols <= 0) return OK;

@@ -43,17 +43,26 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
     }
     if (tid < TS_PB) tau_s[tid] = 0.0;
 
+    // sum of 32 products with 8 independent chains (the FP64 pipe has a long dependent latency)
+#define TS_DOT32(res, EXPR)                                                     \
+    {                                                                           \
+        double _p[8];                                                           \
+        _Pragma("unroll") for (int _k = 0; _k < 8; _k++) { int i = _k; _p[_k] = (EXPR); } \
+        _Pragma("unroll") for (int _q = 1; _q < 4; _q++)                        \
+            _Pragma("unroll") for (int _k = 0; _k < 8; _k++) { int i = _q * 8 + _k; _p[_k] += (EXPR); } \
+        res = ((_p[0] + _p[1]) + (_p[2] + _p[3])) + ((_p[4] + _p[5]) + (_p[6] + _p[7])); \
+    }
+
+    // norm data of column 0 (later columns get theirs at the end of the previous step)
+    if (c == 0) {
+        double pn;
+        TS_DOT32(pn, (rbase + i > 0) ? x[i] * x[i] : 0.0);
+        partn[w] = pn;
+        if (w == 0) alpha_s = x[0];
+    }
+    __syncthreads();
     for (int j = 0; j < nref; j++) {
-        // ---- reflector j from column j, rows >= j
-        if (c == j) {
-            double pn = 0.0;
-#pragma unroll
-            for (int i = 0; i < 32; i++) pn += (rbase + i > j) ? x[i] * x[i] : 0.0;
-            partn[w] = pn;
-#pragma unroll
-            for (int i = 0; i < 32; i++) if (rbase + i == j) alpha_s = x[i];
-        }
-        __syncthreads();
+        // ---- reflector j from column j, rows >= j   (partn / alpha_s were produced by the previous step)
         double ss = 0.0;
 #pragma unroll
         for (int k = 0; k < TS_NW; k++) ss += partn[k];
@@ -77,9 +86,8 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
         }
         __syncthreads();
         // ---- apply H_j to the trailing columns
-        double dsum = 0.0;
-#pragma unroll
-        for (int i = 0; i < 32; i++) dsum += v_s[rbase + i] * x[i];
+        double dsum;
+        TS_DOT32(dsum, v_s[rbase + i] * x[i]);
         part[w][c] = dsum;
         __syncthreads();
         if (c > j && c < b) {
@@ -89,7 +97,15 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             wc *= tau;
 #pragma unroll
             for (int i = 0; i < 32; i++) x[i] -= v_s[rbase + i] * wc;
+            if (c == j + 1) {   // norm data of the next pivot column
+                double pn;
+                TS_DOT32(pn, (rbase + i > j + 1) ? x[i] * x[i] : 0.0);
+                partn[w] = pn;
+#pragma unroll
+                for (int i = 0; i < 32; i++) if (rbase + i == j + 1) alpha_s = x[i];
+            }
         }
+        __syncthreads();
     }
     __syncthreads();
     // reflectors (and R) back to P; R block (b x b, zero below the diagonal / beyond rows) to the stack
@@ -133,9 +149,8 @@ tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, cons
     int buf = 0;
     for (int j = nref - 1; j >= 0; j--) {
         const double* v = Vs + j * VP + rbase;
-        double dsum = 0.0;
-#pragma unroll
-        for (int i = 0; i < 32; i++) dsum += v[i] * z[i];
+        double dsum;
+        TS_DOT32(dsum, v[i] * z[i]);
         double* pb = part + buf * TS_NW * TS_PB;
         pb[w * TS_PB + c] = dsum;
         __syncthreads();

@@ -25,11 +25,14 @@ def _require_cuda(*tensors):
     return dev
 
 
-def _ws(dev, nbytes):
-    """Per-device grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+def _ws(dev, nbytes, stream=None):
+    """Per-(device, stream) grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
+    sid = 0 if stream is None else stream.cuda_stream
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), sid)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            torch.cuda.synchronize(dev)      # rare (grow-only): kernels of any stream may still use the old buffer
         _workspaces[key] = None
         buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=dev)
         _workspaces[key] = buf
@@ -44,7 +47,10 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _stream(dev):
+def _stream(dev, stream=None):
+    """cudaStream_t handed to the library: an explicit side stream, or torch's current stream."""
+    if stream is not None:
+        return ctypes.c_void_p(stream.cuda_stream)
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
@@ -87,8 +93,9 @@ def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0):
     return gemm_ex(M, N, K, 1, A, B, C, idx, force_tile=force_tile, force_splitk=force_splitk)
 
 
-def quarter_tensor(C, E2, E1, A_view, normalize=True):
-    """projectors.py:36-60.  C (xa,xb), E2 (xb,xc,D,D), E1 (xe,xa,D,D), A_view = bond_permute(k) (strided view)."""
+def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None):
+    """projectors.py:36-60.  C (xa,xb), E2 (xb,xc,D,D), E1 (xe,xa,D,D), A_view = bond_permute(k) (strided view).
+    absmax: optional 1-element device tensor receiving max|Q| of the un-normalised tensor."""
     dev = _require_cuda(C, E2, E1, A_view)
     C, E2, E1 = C.contiguous(), E2.contiguous(), E1.contiguous()
     xa, xb = C.shape
@@ -100,10 +107,11 @@ def quarter_tensor(C, E2, E1, A_view, normalize=True):
     lib = _lib.load()
     Q = torch.empty(xc * D * D, xe * D * D, dtype=torch.float64, device=dev)
     nb = lib.acetn_b200_quarter_tensor_workspace_bytes(xa, xb, xc, xe, D, d)
-    ws = _ws(dev, nb)
+    ws = _ws(dev, nb, stream)
     with torch.cuda.device(dev):
         st = lib.acetn_b200_quarter_tensor(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
-                                           1 if normalize else 0, _p(Q), _p(ws), ws.numel(), _stream(dev))
+                                           1 if normalize else 0, _p(Q), _p(absmax) if absmax is not None else None, _p(ws), ws.numel(),
+                                           _stream(dev, stream))
     _lib.check(st, "quarter_tensor")
     return Q, (xc, D, D, xe, D, D)
 
@@ -141,7 +149,7 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     return S, Wt, Jt, info
 
 
-def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12):
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None):
     """Randomized SVD of mats[0] @ ... @ mats[-1] with the caller's test matrix omega (n, q).
     Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps])."""
     dev = _require_cuda(*mats, omega)
@@ -161,18 +169,19 @@ def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12):
     info = torch.zeros(2, dtype=torch.int32, device=dev)
     r_arr, c_arr = _lib.i64_array(rows), _lib.i64_array(cols)
     nb = lib.acetn_b200_rsvd_workspace_bytes(nmat, r_arr, c_arr, q)
-    ws = _ws(dev, nb)
+    ws = _ws(dev, nb, stream)
     ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() for t in mats])
     with torch.cuda.device(dev):
         st = lib.acetn_b200_rsvd(nmat, ptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
                                  q if chi is None else int(chi), float(cutoff), _p(U), _p(S), _p(V), _p(info), _p(ws), ws.numel(),
-                                 _stream(dev))
+                                 _stream(dev, stream))
     _lib.check(st, "rsvd")
     return U, S, V, info
 
 
-def projectors_from_usv(Q1, Q4, U, V, S, keep):
-    """projectors.py:166-173. Q1 (m1,n1), Q4 (m4,n4), U (m1,q), V (n4,q). Returns proj1 (n1,keep), proj2 (m4,keep)."""
+def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=None):
+    """projectors.py:166-173. Q1 (m1,n1), Q4 (m4,n4), U (m1,q), V (n4,q). Returns proj1 (n1,keep), proj2 (m4,keep).
+    qmax1/qmax4: max|Q| scalars of un-normalised Q1/Q4 (see acetn_b200.h)."""
     dev = _require_cuda(Q1, Q4, U, V, S)
     m1, n1 = Q1.shape
     m4, n4 = Q4.shape
@@ -180,10 +189,11 @@ def projectors_from_usv(Q1, Q4, U, V, S, keep):
     p1 = torch.empty(n1, keep, dtype=torch.float64, device=dev)
     p2 = torch.empty(m4, keep, dtype=torch.float64, device=dev)
     nb = lib.acetn_b200_projectors_workspace_bytes(m1, n1, m4, n4, keep)
-    ws = _ws(dev, nb)
+    ws = _ws(dev, nb, stream)
     with torch.cuda.device(dev):
         st = lib.acetn_b200_projectors_from_usv(_p(Q1), m1, n1, _p(Q4), m4, n4, _p(U), U.stride(0), _p(V), V.stride(0), _p(S), keep,
-                                                _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev))
+                                                _p(qmax1) if qmax1 is not None else None, _p(qmax4) if qmax4 is not None else None,
+                                                _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev, stream))
     _lib.check(st, "projectors_from_usv")
     return p1, p2
 

@@ -10,7 +10,12 @@ from . import linalg, ops
 
 
 class ProjectorCalculator:
-    """acetn/renormalization/projectors.py:6-236."""
+    """acetn/renormalization/projectors.py:6-236.
+
+    `calculate(ipeps, sites, k)` has the reference's signature.  Internally a projector is computed in two phases so
+    that the independent site tasks of one directional move can be put on different CUDA streams:
+    `begin(...)` enqueues quarter tensors + randomized SVD (no host sync), `finish(pending)` reads the truncated
+    rank chi' (the reference's one host sync per projector, projectors.py:164) and enqueues the projector GEMMs."""
 
     def __init__(self, config):
         self.projectors = config.projectors
@@ -24,106 +29,207 @@ class ProjectorCalculator:
     def set_calculate(self):
         if self.projectors is None or self.projectors == "full-system":
             self.calculate = self.calculate_full_system
+            self.begin = self.begin_full_system
         elif self.projectors == "half-system":
             self.calculate = self.calculate_half_system
+            self.begin = self.begin_half_system
         else:
             raise ValueError(f"Invalid ctmrg projector type: {self.projectors} provided.")
 
     @staticmethod
-    def make_quarter_tensor(site_tensor, k):
-        """projectors.py:36-60 -> (Q matrix (chi D^2, chi D^2), 6-tuple shape)."""
+    def make_quarter_tensor(site_tensor, k, normalize=True, stream=None, absmax=None):
+        """projectors.py:36-60 -> (Q matrix (chi D^2, chi D^2), 6-tuple shape).
+        normalize=False skips the max-abs division (projectors.py:59): s/s[0], U and V are invariant under a rescaling
+        of Q1/Q4, and the internal callers re-apply the factor 1/max|Q| to the small projector instead (absmax), which
+        saves two passes over the 2 GiB tensor and reproduces the reference's projectors exactly."""
         ak = site_tensor.bond_permute(k)
         ck = site_tensor['C'][(0 + k) % 4]
         ek1 = site_tensor['E'][(3 + k) % 4]
         ek2 = site_tensor['E'][(0 + k) % 4]
-        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=True)
+        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax)
 
-    def _truncate(self, S, info, chi):
-        # projectors.py:163-164 : s/=s[0]; chi' = min(chi, #{s > cutoff}) -- the one host sync per projector
-        keep = int(info[0].item())
+    def _check_svd_type(self):
+        if self.svd_type == "full-rank":
+            raise NotImplementedError("backend='b200': svd_type='full-rank' is not implemented (use 'rsvd')")
+        if self.svd_type != "rsvd":
+            raise ValueError(f"Invalid svd_type: {self.svd_type} provided.")
+
+    # ---- phase 1 ------------------------------------------------------------------------------------------------
+    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None):
+        """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed)."""
+        self._check_svd_type()
+        s1, s4 = sites[0], sites[3]
+        st1, st4 = ipeps[s1], ipeps[s4]
+        chi = ipeps.dims["chi"]
+        if omega is None:
+            omega = self.draw_omega(ipeps, sites, k)
+        mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
+        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=stream, absmax=mx[0:1])
+        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=stream, absmax=mx[1:2])
+        U, S, V, info = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi, cutoff=self.svd_cutoff,
+                                 stream=stream)
+        return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": U, "S": S, "V": V, "info": info, "omega": omega,
+                "stream": stream}
+
+    def begin_full_system(self, ipeps, sites, k, stream=None, omega=None):
+        """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
+        self._check_svd_type()
+        s1, s2, s3, s4 = sites
+        chi = ipeps.dims["chi"]
+        if omega is None:
+            omega = self.draw_omega(ipeps, sites, k)
+        Q1, q1D = self.make_quarter_tensor(ipeps[s1], k, normalize=True, stream=stream)
+        Q2, _ = self.make_quarter_tensor(ipeps[s2], k + 1, normalize=True, stream=stream)
+        Q3, _ = self.make_quarter_tensor(ipeps[s3], k + 2, normalize=True, stream=stream)
+        Q4, q4D = self.make_quarter_tensor(ipeps[s4], k + 3, normalize=True, stream=stream)
+        U, S, V, info = ops.rsvd([Q2, Q1, Q4, Q3], omega, niter=self.rsvd_niter, reorth_adjoint=True, chi=chi,
+                                 cutoff=self.svd_cutoff, stream=stream)
+        return {"kind": "full", "Q1": Q1, "Q2": Q2, "Q3": Q3, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": U, "S": S, "V": V,
+                "info": info, "omega": omega, "stream": stream}
+
+    def draw_omega(self, ipeps, sites, k):
+        """The Gaussian test matrix of this projector, drawn exactly where/how the reference draws it
+        (torch.randn(n, q) on the tensors' device, fused_matmul_svd_lowrank.py:32): one draw per projector, in call order."""
+        chi = ipeps.dims["chi"]
+        D = ipeps.dims["bond"]
+        if self.projectors == "half-system":
+            st1, st4 = ipeps[sites[0]], ipeps[sites[3]]
+            m = st1['E'][(0 + k) % 4].shape[1] * D * D            # rows of Q1: chi_c of E[k]
+            n = st4['E'][(3 + k + 3) % 4].shape[0] * D * D        # cols of Q4: chi_e of E[(3+(k+3))%4]
+            kdim = st1['E'][(3 + k) % 4].shape[0] * D * D
+            q = min(chi + self.rsvd_oversampling, m, n)
+        else:
+            st2, st3 = ipeps[sites[1]], ipeps[sites[2]]
+            m = st2['E'][(k + 1) % 4].shape[1] * D * D            # rows of Q2
+            n = st3['E'][(3 + k + 2) % 4].shape[0] * D * D        # cols of Q3
+            q = min(chi + self.rsvd_oversampling, m, n)
+        A = ipeps[sites[0]]['A']
+        return linalg._omega(n, q, A.dtype, A.device)
+
+    # ---- phase 2 ------------------------------------------------------------------------------------------------
+    def finish(self, pend):
+        stream = pend["stream"]
+        if stream is not None:
+            stream.synchronize()
+        keep = int(pend["info"][0].item())   # projectors.py:163-164 : the one host sync per projector
+        S = pend["S"]
         if self.spectra is not None:
             self.spectra.append((S / S[0]).detach().cpu())
-        return keep
+        q1D, q4D = pend["q1D"], pend["q4D"]
+        if pend["kind"] == "half":
+            mx = pend["mx"]
+            p1, p2 = ops.projectors_from_usv(pend["Q1"], pend["Q4"], pend["U"], pend["V"], S, keep, stream=stream,
+                                             qmax1=mx[0:1], qmax4=mx[1:2])
+        else:
+            # projectors.py:209-217 : proj1 = Q1^H (Q2^H conj(U)), proj2 = Q4 (Q3 V), columns scaled by s^-1/2
+            # (runs on the main stream; finish() already synchronised the side stream)
+            w = 1.0 / torch.sqrt(S[:keep] / S[0])
+            Us = (pend["U"][:, :keep] * w).contiguous()
+            Vs = (pend["V"][:, :keep] * w).contiguous()
+            p1 = ops.matmul(pend["Q1"], ops.matmul(pend["Q2"], Us, transpose_a=True), transpose_a=True)
+            p2 = ops.matmul(pend["Q4"], ops.matmul(pend["Q3"], Vs))
+        return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
 
     def calculate_half_system(self, ipeps, sites, k):
         """projectors.py:138-174."""
-        if self.svd_type == "full-rank":
-            raise NotImplementedError("backend='b200': svd_type='full-rank' is not implemented (use 'rsvd')")
-        s1, s4 = sites[0], sites[3]
-        Q1, q1D = self.make_quarter_tensor(ipeps[s1], k)
-        Q4, q4D = self.make_quarter_tensor(ipeps[s4], k + 3)
-        chi = ipeps.dims["chi"]
-        q = min(chi + self.rsvd_oversampling, Q1.shape[0], Q4.shape[1])
-        omega = linalg._omega(Q4.shape[1], q, Q1.dtype, Q1.device)
-        U, S, V, info = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi, cutoff=self.svd_cutoff)
-        keep = self._truncate(S, info, chi)
-        p1, p2 = ops.projectors_from_usv(Q1, Q4, U, V, S, keep)
-        return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
+        return self.finish(self.begin_half_system(ipeps, sites, k))
 
     def calculate_full_system(self, ipeps, sites, k):
-        """projectors.py:176-217 (rsvd branch): rSVD of (Q2 Q1)(Q4 Q3), proj1 = Q1^H (Q2^H conj(U)), proj2 = Q4 (Q3 V)."""
-        if self.svd_type == "full-rank":
-            raise NotImplementedError("backend='b200': svd_type='full-rank' is not implemented (use 'rsvd')")
-        s1, s2, s3, s4 = sites
-        Q1, q1D = self.make_quarter_tensor(ipeps[s1], k)
-        Q2, _ = self.make_quarter_tensor(ipeps[s2], k + 1)
-        Q3, _ = self.make_quarter_tensor(ipeps[s3], k + 2)
-        Q4, q4D = self.make_quarter_tensor(ipeps[s4], k + 3)
-        chi = ipeps.dims["chi"]
-        q = min(chi + self.rsvd_oversampling, Q2.shape[0], Q3.shape[1])
-        omega = linalg._omega(Q3.shape[1], q, Q1.dtype, Q1.device)
-        U, S, V, info = ops.rsvd([Q2, Q1, Q4, Q3], omega, niter=self.rsvd_niter, reorth_adjoint=True, chi=chi, cutoff=self.svd_cutoff)
-        keep = self._truncate(S, info, chi)
-        w = 1.0 / torch.sqrt(S[:keep] / S[0])
-        Us = (U[:, :keep] * w).contiguous()
-        Vs = (V[:, :keep] * w).contiguous()
-        p1 = ops.matmul(Q1, ops.matmul(Q2, Us, transpose_a=True), transpose_a=True)
-        p2 = ops.matmul(Q4, ops.matmul(Q3, Vs))
-        return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
+        """projectors.py:176-217 (rsvd branch)."""
+        return self.finish(self.begin_full_system(ipeps, sites, k))
 
 
 class DirectionalMover:
-    """acetn/renormalization/directional_mover.py:5-366 (non-distributed moves)."""
+    """acetn/renormalization/directional_mover.py:5-366 (non-distributed moves).
 
-    def __init__(self, config):
+    The ny (nx) projector computations of a move are independent (directional_mover.py:23-40 computes them in a plain
+    loop); here they are enqueued round-robin on `n_streams` CUDA streams so that one site's latency-bound stages
+    (TSQR panels, Jacobi core) overlap the other site's DGEMMs.  Omega is still drawn in the reference's order."""
+
+    def __init__(self, config, n_streams=None):
         self.projector_calculator = ProjectorCalculator(config)
         self.calculate_projectors = self.projector_calculator.calculate
+        import os
+        self.n_streams = int(os.environ.get("ACETN_B200_STREAMS", "2")) if n_streams is None else n_streams
+        self._streams = None
+
+    def _side_streams(self, device):
+        if self.n_streams <= 1:
+            return [None]
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
+        return self._streams
+
+    def _projectors_of_line(self, ipeps, plaquettes, k):
+        """All projector pairs of one move: {key: (proj1, proj2)} ; plaquettes = [(key, sites)]."""
+        pc = self.projector_calculator
+        device = ipeps[plaquettes[0][1][0]]['A'].device
+        if device.type != "cuda":
+            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        streams = self._side_streams(device)
+        omegas = [pc.draw_omega(ipeps, sites, k) for _, sites in plaquettes]     # reference order of the RNG draws
+        main = torch.cuda.current_stream(device)
+        for st in streams:
+            if st is not None:
+                st.wait_stream(main)
+        pend = [pc.begin(ipeps, sites, k, stream=streams[i % len(streams)], omega=omegas[i])
+                for i, (_, sites) in enumerate(plaquettes)]
+        out = {}
+        for (key, _), pd in zip(plaquettes, pend):
+            out[key] = pc.finish(pd)
+        for st in streams:
+            if st is not None:
+                main.wait_stream(st)
+        del pend                     # Q tensors are released only after the main stream is ordered behind the side streams
+        return {key: v[0] for key, v in out.items()}, {key: v[1] for key, v in out.items()}
 
     # ---- the four moves (directional_mover.py:23-97) -----------------------------------------------------------
     def left_move(self, ipeps, xi):
-        proj1, proj2 = {}, {}
-        for yi in range(ipeps.ny):
-            proj1[yi], proj2[yi] = self.calculate_left_projectors(ipeps, xi, yi)
-        for yi in range(ipeps.ny):
-            xj = (xi + 1) % ipeps.nx
-            yj = (yi + 1) % ipeps.ny
+        nx, ny = ipeps.nx, ipeps.ny
+        plaq = []
+        for yi in range(ny):
+            xj, yj = (xi + 1) % nx, (yi - 1 + ny) % ny
+            plaq.append((yi, [(xi, yi), (xj, yi), (xj, yj), (xi, yj)]))
+        proj1, proj2 = self._projectors_of_line(ipeps, plaq, 0)
+        for yi in range(ny):
+            xj = (xi + 1) % nx
+            yj = (yi + 1) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xj, yi), yi, yj, k=0)
 
     def up_move(self, ipeps, yi):
-        proj1, proj2 = {}, {}
-        for xi in range(ipeps.nx):
-            proj1[xi], proj2[xi] = self.calculate_up_projectors(ipeps, xi, yi)
-        for xi in range(ipeps.nx):
-            xj = (xi + 1) % ipeps.nx
-            yj = (yi - 1 + ipeps.ny) % ipeps.ny
+        nx, ny = ipeps.nx, ipeps.ny
+        plaq = []
+        for xi in range(nx):
+            xj, yj = (xi - 1 + nx) % nx, (yi - 1 + ny) % ny
+            plaq.append((xi, [(xi, yi), (xi, yj), (xj, yj), (xj, yi)]))
+        proj1, proj2 = self._projectors_of_line(ipeps, plaq, 1)
+        for xi in range(nx):
+            xj = (xi + 1) % nx
+            yj = (yi - 1 + ny) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xi, yj), xi, xj, k=1)
 
     def right_move(self, ipeps, xi):
-        proj1, proj2 = {}, {}
-        for yi in range(ipeps.ny):
-            proj1[yi], proj2[yi] = self.calculate_right_projectors(ipeps, xi, yi)
-        for yi in range(ipeps.ny):
-            xj = (xi - 1 + ipeps.nx) % ipeps.nx
-            yj = (yi - 1 + ipeps.ny) % ipeps.ny
+        nx, ny = ipeps.nx, ipeps.ny
+        plaq = []
+        for yi in range(ny):
+            xj, yj = (xi - 1 + nx) % nx, (yi + 1) % ny
+            plaq.append((yi, [(xi, yi), (xj, yi), (xj, yj), (xi, yj)]))
+        proj1, proj2 = self._projectors_of_line(ipeps, plaq, 2)
+        for yi in range(ny):
+            xj = (xi - 1 + nx) % nx
+            yj = (yi - 1 + ny) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xj, yi), yi, yj, k=2)
 
     def down_move(self, ipeps, yi):
-        proj1, proj2 = {}, {}
-        for xi in range(ipeps.nx):
-            proj1[xi], proj2[xi] = self.calculate_down_projectors(ipeps, xi, yi)
-        for xi in range(ipeps.nx):
-            xj = (xi - 1 + ipeps.nx) % ipeps.nx
-            yj = (yi + 1) % ipeps.ny
+        nx, ny = ipeps.nx, ipeps.ny
+        plaq = []
+        for xi in range(nx):
+            xj, yj = (xi + 1) % nx, (yi + 1) % ny
+            plaq.append((xi, [(xi, yi), (xi, yj), (xj, yj), (xj, yi)]))
+        proj1, proj2 = self._projectors_of_line(ipeps, plaq, 3)
+        for xi in range(nx):
+            xj = (xi - 1 + nx) % nx
+            yj = (yi + 1) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xi, yj), xi, xj, k=3)
 
     # ---- plaquette pickers (directional_mover.py:99-181) ----------------------------------------------------------

@@ -61,12 +61,14 @@ int acetn_b200_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, const double
  *   Q[(c,r,R),(e,d,D)] = sum C[a,b] E2[b,c,u,U] E1[e,a,l,L] conj(A)[L,U,R,D,P] A[l,u,r,d,P],  then Q /= max|Q|
  *   C  (chi_a, chi_b) = site.C[k];  E2 (chi_b, chi_c, D, D) = site.E[k];  E1 (chi_e, chi_a, D, D) = site.E[(3+k)%4]
  *   A  = site.bond_permute(k), a strided view: a_strides[5] in elements for legs (l,u,r,d,p) of the view.
- *   Q out: (chi_c*D*D) x (chi_e*D*D) row-major.  normalize != 0 applies the max-abs division (projectors.py:59). */
+ *   Q out: (chi_c*D*D) x (chi_e*D*D) row-major.  normalize != 0 applies the max-abs division (projectors.py:59).
+ *   absmax_out (device double, may be NULL): receives max|Q| of the un-normalised tensor. */
 size_t acetn_b200_quarter_tensor_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_e,
                                                  int64_t D, int64_t d);
 int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E1, const double* A,
                               const int64_t* a_strides, int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_e,
-                              int64_t D, int64_t d, int normalize, double* Q, void* ws, size_t ws_bytes, void* stream);
+                              int64_t D, int64_t d, int normalize, double* Q, double* absmax_out, void* ws, size_t ws_bytes,
+                              void* stream);
 
 /* ---- randomized SVD family: acetn/linalg/{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}.py
  *   rSVD of the product M_0 M_1 ... M_{nmat-1} (nmat = 1, 2 or 4) without forming it.  mats[i] is rows[i] x cols[i]
@@ -93,11 +95,15 @@ int acetn_b200_jacobi_svd(const double* R, int64_t q, double* S, double* Wt, dou
 /* ---- projector formation: projectors.py:166-173 (half-system) ---------------------------------------------------
  *   proj1[(e,d,D), z] = sum_x Q1[x,(e,d,D)] U[x,z] w[z],  proj2[(c,u,U), z] = sum_y Q4[(c,u,U),y] V[y,z] w[z],
  *   w[z] = (S[z]/S[0])^-1/2, z < keep.   Q1: m1 x n1, Q4: m4 x n4, U: m1 x ldu, V: n4 x ldv.
- *   proj1 out: n1 x keep, proj2 out: m4 x keep. */
+ *   proj1 out: n1 x keep, proj2 out: m4 x keep.
+ *   qmax1 / qmax4 (device doubles, may be NULL): when Q1 / Q4 were produced with normalize = 0, passing their max|Q|
+ *   here divides proj1 / proj2 by it, which reproduces the reference's normalised-Q projectors exactly while saving the
+ *   two HBM passes of the division over the 2 GiB tensors. */
 size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep);
 int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
                                    const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S,
-                                   int64_t keep, double* proj1, double* proj2, void* ws, size_t ws_bytes, void* stream);
+                                   int64_t keep, const double* qmax1, const double* qmax4, double* proj1, double* proj2,
+                                   void* ws, size_t ws_bytes, void* stream);
 
 /* ---- absorption: DirectionalMover.renormalize_cj1/cj2/ej, acetn/renormalization/directional_mover.py:306-366 ---
  *   corner1: out[a,x] = sum ei[a,b,l,L] ci[b,c] proj[c,l,L,x] / ||.||     ci (chi_b,chi_c) ei (chi_a,chi_b,D,D) proj (chi_c,D,D,chi_x)
