@@ -1,15 +1,182 @@
-// K2 (fused form): double-layer site absorption with the intermediate kept on chip.  (specialisations are added per (D,d))
+// K2 (fused form): double-layer site absorption with the intermediate kept on chip (Q.s3+Q.s4,
+// E.2+E.3 -- reference acetn/renormalization/projectors.py:54-55 and directional_mover.py:363-364).
+//
+// Per (chi,chi) block:  Y[(r,R),(d,D)] = sum_{i0,I0,i1,I1,p} X[i0,I0,i1,I1] * conj(A)[I.,I.,R,D,p] * A[i.,i.,r,d,p]
+// done as two DMMA GEMMs whose intermediate W never leaves the register file:
+//   step 1  W^T[(p,y),(i0,i1)] = sum_{(I0,I1)} S[(I0,I1)][p][y] * X[(i0,I0),(i1,I1)]          y = (R,D)
+//   step 2  Y[y, n]            = sum_{(i0,i1),p} W^T[(p,y),(i0,i1)] * S[(i0,i1)][p][n]         n = (r,d)
+// The accumulator fragment of step 1 (row lane/4, columns 2*(lane%4)+{0,1}) is turned into the A fragment of step 2
+// with two warp shuffles per k-step; S (the site tensor, 64 KiB at D=8,d=2, one copy serves bra and ket because the
+// path is real FP64) stays in shared memory for the lifetime of a persistent CTA, X blocks stream through a
+// double-buffered cp.async stage.  Algorithmic HBM traffic per block: D^4*8 B in + D^4*8 B out (32 flop/B at D=8).
+//
+// Specialised for D = 8, d = 2 (the headline configuration); other shapes use the unfused two-GEMM form in api.cu.
 #include "kernels.cuh"
 
 namespace ab200 {
 
-int double_layer_fused_supported(int64_t D, int64_t d) { (void)D; (void)d; return 0; }
+namespace {
+constexpr int FD = 8, FD2 = 64, Fd = 2;
+constexpr int S_PX = Fd * FD2 + 4;        // 132: pitch of the pair index x  (== 4 mod 16 -> conflict-free fragments)
+constexpr int S_PP = FD2;                 // pitch of the physical index
+constexpr int X_ROW = 96;                 // X stage row pitch: 8 groups (i1) of 8 (+4 pad) doubles
+constexpr int X_I1 = 12;
+constexpr int S_ELEMS = FD2 * S_PX;       // 8448
+constexpr int X_ELEMS = FD2 * X_ROW;      // 6144
+constexpr size_t FUSED_SMEM = (size_t)(S_ELEMS + 2 * X_ELEMS) * sizeof(double);
+constexpr int F_THREADS = 256;
+
+struct FusedParams {
+    const double* X; int64_t n0, n1, in_s0, in_s1, es0, es1, es2;
+    const double* A; int64_t ax0, ax1, ap, ay0, ay1;       // strides of A for x=(f0,f1), p, y=(r,d)
+    double* Y; int64_t out_s0, out_s1, oes0, oes1, oes2, oes3;
+    double* absmax;
+};
+
+__global__ void __launch_bounds__(F_THREADS, 1) double_layer_fused_d8_kernel(const FusedParams p) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;
+    double* Xs = sm + S_ELEMS;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int64_t nblk = p.n0 * p.n1;
+
+    // ---- site tensor -> S[x][p][y]
+    for (int idx = tid; idx < FD2 * Fd * FD2; idx += F_THREADS) {
+        int y = idx & 63, pp = (idx >> 6) & 1, x = idx >> 7;
+        S[x * S_PX + pp * S_PP + y] =
+            p.A[(x >> 3) * p.ax0 + (x & 7) * p.ax1 + pp * p.ap + (y >> 3) * p.ay0 + (y & 7) * p.ay1];
+    }
+
+    // ---- X stage loader: thread -> (I0 = w, i1 = (lane>>2), pair = lane&3), 8 chunks over i0
+    const int64_t x_thread = (int64_t)w * p.es1 + (int64_t)(lane >> 2) * p.es2 + 2 * (lane & 3);
+    const uint32_t xs_base = smem_u32(Xs);
+    const uint32_t xs_thread = (uint32_t)((w * X_ROW + (lane >> 2) * X_I1 + 2 * (lane & 3)) * 8);
+    auto load_block = [&](int64_t blk, int buf) {
+        const int64_t b0 = blk / p.n1, b1 = blk - b0 * p.n1;
+        const double* src = p.X + b0 * p.in_s0 + b1 * p.in_s1 + x_thread;
+        const uint32_t dst = xs_base + (uint32_t)(buf * X_ELEMS * 8) + xs_thread;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(i * 8 * X_ROW * 8)), "l"(src + i * p.es0));
+    };
+
+    double vmax = 0.0;
+    int64_t blk = blockIdx.x;
+    if (blk < nblk) load_block(blk, 0);
+    cp_async_commit();
+    int buf = 0;
+    for (; blk < nblk; blk += gridDim.x, buf ^= 1) {
+        const int64_t nxt = blk + gridDim.x;
+        if (nxt < nblk) load_block(nxt, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* Xb = Xs + buf * X_ELEMS;
+
+        // ---- step 1: acc1[P][j] = W^T[(P, y = 8w+lr), x = 8j + 2lc + {0,1}]
+        double acc1[2][8][2];
+#pragma unroll
+        for (int P = 0; P < 2; P++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) { acc1[P][j][0] = 0.0; acc1[P][j][1] = 0.0; }
+        const double* Sa = S + lc * S_PX + 8 * w + lr;           // + 4*ks*S_PX + P*S_PP
+        const double* Xf = Xb + lr * X_I1 + lc;                  // + (8j + (ks>>1))*X_ROW + (ks&1)*4
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++) {
+            double a0 = Sa[4 * ks * S_PX], a1 = Sa[4 * ks * S_PX + S_PP];
+            double bfr[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) bfr[j] = Xf[(8 * j + (ks >> 1)) * X_ROW + (ks & 1) * 4];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                dmma884(acc1[0][j][0], acc1[0][j][1], a0, bfr[j]);
+                dmma884(acc1[1][j][0], acc1[1][j][1], a1, bfr[j]);
+            }
+        }
+
+        // ---- step 2: acc2[jn] = Y[y = 8w+lr, n = 8jn + 2lc + {0,1}]
+        double acc2[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { acc2[j][0] = 0.0; acc2[j][1] = 0.0; }
+        const double* Sb = S + lc * S_PX + lr;                   // + x0*S_PX + P*S_PP + 8*jn
+#pragma unroll
+        for (int P = 0; P < 2; P++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    // A fragment of step 2: W^T[(P,y), x0 + lc], x0 = 8j + 4h, lives in lane (lr, 2h + lc/2), register lc&1
+                    const int srcl = (lane & ~3) | (2 * h + (lc >> 1));
+                    double v0 = __shfl_sync(0xffffffffu, acc1[P][j][0], srcl);
+                    double v1 = __shfl_sync(0xffffffffu, acc1[P][j][1], srcl);
+                    double a = (lc & 1) ? v1 : v0;
+                    const double* sb = Sb + (8 * j + 4 * h) * S_PX + P * S_PP;
+                    double bfr[8];
+#pragma unroll
+                    for (int jn = 0; jn < 8; jn++) bfr[jn] = sb[8 * jn];
+#pragma unroll
+                    for (int jn = 0; jn < 8; jn++) dmma884(acc2[jn][0], acc2[jn][1], a, bfr[jn]);
+                }
+            }
+        }
+
+        // ---- store: y = (R = w, Dd = lr), n = (r = jn, dd = 2lc + e)
+        {
+            const int64_t b0 = blk / p.n1, b1 = blk - b0 * p.n1;
+            double* Yb = p.Y + b0 * p.out_s0 + b1 * p.out_s1 + (int64_t)w * p.oes1 + (int64_t)lr * p.oes3;
+#pragma unroll
+            for (int jn = 0; jn < 8; jn++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double v = acc2[jn][e];
+                    Yb[(int64_t)jn * p.oes0 + (int64_t)(2 * lc + e) * p.oes2] = v;
+                    vmax = fmax(vmax, fabs(v));
+                }
+            }
+        }
+        __syncthreads();     // all warps are done with Xs[buf] before the next iteration refills it
+    }
+    cp_async_wait<0>();
+    if (p.absmax) {
+        vmax = warp_max(vmax);
+        if (lane == 0) atomic_max_nonneg(p.absmax, vmax);
+    }
+}
+}  // namespace
+
+int double_layer_fused_supported(int64_t D, int64_t d) { return (D == 8 && d == 2) ? 1 : 0; }
 
 int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t in_s0, int64_t in_s1, const int64_t* in_es,
                               int order, const double* A, const int64_t* a_strides, int64_t D, int64_t d, double* Y,
                               int64_t out_s0, int64_t out_s1, const int64_t* out_es, double* absmax, cudaStream_t s) {
-    set_error("double_layer_fused: no specialisation for D=%lld d=%lld", (long long)D, (long long)d);
-    return ERR_UNSUPPORTED;
+    if (!double_layer_fused_supported(D, d)) {
+        set_error("double_layer_fused: no specialisation for D=%lld d=%lld", (long long)D, (long long)d);
+        return ERR_UNSUPPORTED;
+    }
+    AB_REQUIRE(in_es[3] == 1, "double_layer_fused: innermost input leg must have unit stride");
+    AB_REQUIRE((((uintptr_t)X) & 15) == 0 && (in_s0 % 2) == 0 && (in_s1 % 2) == 0 && (in_es[0] % 2) == 0 && (in_es[1] % 2) == 0 &&
+                   (in_es[2] % 2) == 0,
+               "double_layer_fused: input block addressing must be 16-byte aligned");
+    static bool configured = false;
+    if (!configured) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(double_layer_fused_d8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM));
+        configured = true;
+    }
+    FusedParams p;
+    p.X = X; p.n0 = n0; p.n1 = n1; p.in_s0 = in_s0; p.in_s1 = in_s1; p.es0 = in_es[0]; p.es1 = in_es[1]; p.es2 = in_es[2];
+    // legs of the A view: 0=l 1=u 2=r 3=d 4=p ; order 0: (i0,i1) = (u,l) ; order 1: (i0,i1) = (l,u)
+    const int f0 = order == 0 ? 1 : 0, f1 = order == 0 ? 0 : 1;
+    p.A = A; p.ax0 = a_strides[f0]; p.ax1 = a_strides[f1]; p.ap = a_strides[4]; p.ay0 = a_strides[2]; p.ay1 = a_strides[3];
+    p.Y = Y; p.out_s0 = out_s0; p.out_s1 = out_s1; p.oes0 = out_es[0]; p.oes1 = out_es[1]; p.oes2 = out_es[2]; p.oes3 = out_es[3];
+    p.absmax = absmax;
+    int64_t nblk = n0 * n1;
+    int grid = device_sm_count();
+    if (nblk < grid) grid = (int)nblk;
+    if (grid < 1) return OK;
+    double_layer_fused_d8_kernel<<<grid, F_THREADS, FUSED_SMEM, s>>>(p);
+    AB_LAUNCHED();
+    return OK;
 }
 
 }  // namespace ab200
