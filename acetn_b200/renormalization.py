@@ -4,6 +4,8 @@ Class/method names, argument meaning, tensor layouts, mutation semantics and err
 (acetn/renormalization/{projectors,directional_mover,ctmrg}.py) so this module drops in behind
 `Ipeps.renormalize()` (see acetn_b200.integration).  All contractions, the randomized SVD and the normalisations
 run in libacetn_b200.so; torch only allocates and draws Omega."""
+import os
+
 import torch
 
 from . import linalg, ops
@@ -149,8 +151,7 @@ class DirectionalMover:
     def __init__(self, config, n_streams=None):
         self.projector_calculator = ProjectorCalculator(config)
         self.calculate_projectors = self.projector_calculator.calculate
-        import os
-        self.n_streams = int(os.environ.get("ACETN_B200_STREAMS", "2")) if n_streams is None else n_streams
+        self.n_streams = int(os.environ.get("ACETN_B200_STREAMS", "4")) if n_streams is None else n_streams
         self._streams = None
 
     def _side_streams(self, device):
@@ -182,6 +183,82 @@ class DirectionalMover:
                 main.wait_stream(st)
         del pend                     # Q tensors are released only after the main stream is ordered behind the side streams
         return {key: v[0] for key, v in out.items()}, {key: v[1] for key, v in out.items()}
+
+    # ---- task view of the moves -----------------------------------------------------------------------------------
+    @staticmethod
+    def move_tasks(ipeps, k, line):
+        """The independent site tasks of one directional move (directional_mover.py:23-97 + pickers :99-181):
+        dicts with the projector plaquette, source/target sites and the projector keys used by renormalize_boundary."""
+        nx, ny = ipeps.nx, ipeps.ny
+        tasks = []
+        if k == 0:
+            for yi in range(ny):
+                xj, yj = (line + 1) % nx, (yi - 1 + ny) % ny
+                tasks.append(dict(k=0, line=line, key=yi, plaq=[(line, yi), (xj, yi), (xj, yj), (line, yj)], s1=(line, yi),
+                                  s2=(xj, yi), i=yi, j=(yi + 1) % ny))
+        elif k == 2:
+            for yi in range(ny):
+                xj, yj = (line - 1 + nx) % nx, (yi + 1) % ny
+                tasks.append(dict(k=2, line=line, key=yi, plaq=[(line, yi), (xj, yi), (xj, yj), (line, yj)], s1=(line, yi),
+                                  s2=(xj, yi), i=yi, j=(yi - 1 + ny) % ny))
+        elif k == 1:
+            for xi in range(nx):
+                xj, yj = (xi - 1 + nx) % nx, (line - 1 + ny) % ny
+                tasks.append(dict(k=1, line=line, key=xi, plaq=[(xi, line), (xi, yj), (xj, yj), (xj, line)], s1=(xi, line),
+                                  s2=(xi, yj), i=xi, j=(xi + 1) % nx))
+        elif k == 3:
+            for xi in range(nx):
+                xj, yj = (xi + 1) % nx, (line + 1) % ny
+                tasks.append(dict(k=3, line=line, key=xi, plaq=[(xi, line), (xi, yj), (xj, yj), (xj, line)], s1=(xi, line),
+                                  s2=(xi, yj), i=xi, j=(xi - 1 + nx) % nx))
+        else:
+            raise ValueError(f"Invalid bond direction k={k}")
+        return tasks
+
+    def move_pair(self, ipeps, moves):
+        """Several directional moves whose tasks are mutually independent, run as one phase: all projectors (on the
+        side streams), then all absorptions.  In half-system mode a left and a right move (an up and a down move)
+        read and write disjoint boundary tensors, which is what the reference's distributed schedule relies on
+        (directional_mover.py:183-271); the Omega draws keep the sequential order (first move's sites, then the
+        second's)."""
+        tasks = []
+        for k, line in moves:
+            tasks += self.move_tasks(ipeps, k, line)
+        plaq = [((t["k"], t["key"]), t["plaq"]) for t in tasks]
+        p1, p2 = self._projectors_of_tasks(ipeps, tasks)
+        for t in tasks:
+            k = t["k"]
+            self.renormalize_boundary(ipeps, {t["i"]: p1[(k, t["i"])], t["j"]: p1[(k, t["j"])]},
+                                      {t["i"]: p2[(k, t["i"])], t["j"]: p2[(k, t["j"])]}, t["s1"], t["s2"], t["i"], t["j"], k)
+
+    def left_right_move(self, ipeps, x1, x2):
+        """Single-process counterpart of left_right_move_dist (directional_mover.py:183-226)."""
+        self.move_pair(ipeps, [(0, x1), (2, x2)])
+
+    def up_down_move(self, ipeps, y1, y2):
+        """Single-process counterpart of up_down_move_dist (directional_mover.py:228-271)."""
+        self.move_pair(ipeps, [(1, y1), (3, y2)])
+
+    def _projectors_of_tasks(self, ipeps, tasks):
+        pc = self.projector_calculator
+        device = ipeps[tasks[0]["s1"]]['A'].device
+        if device.type != "cuda":
+            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        streams = self._side_streams(device)
+        omegas = [pc.draw_omega(ipeps, t["plaq"], t["k"]) for t in tasks]      # reference order of the RNG draws
+        main = torch.cuda.current_stream(device)
+        for st in streams:
+            if st is not None:
+                st.wait_stream(main)
+        pend = [pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n]) for n, t in enumerate(tasks)]
+        p1, p2 = {}, {}
+        for t, pd in zip(tasks, pend):
+            p1[(t["k"], t["key"])], p2[(t["k"], t["key"])] = pc.finish(pd)
+        for st in streams:
+            if st is not None:
+                main.wait_stream(st)
+        del pend
+        return p1, p2
 
     # ---- the four moves (directional_mover.py:23-97) -----------------------------------------------------------
     def left_move(self, ipeps, xi):
@@ -273,11 +350,19 @@ def ctmrg(ipeps, config, mover=None):
     """acetn/renormalization/ctmrg.py:4-31 (non-distributed ordering; the sharded schedule lives in
     acetn_b200.distributed)."""
     mover = mover or DirectionalMover(config)
+    # half-system: the left/right (up/down) moves of one iteration are independent and are run as one phase
+    paired = config.projectors == "half-system" and os.environ.get("ACETN_B200_PAIR_MOVES", "1") != "0"
     for _ in range(config.steps):
         for xi in range(ipeps.nx):
-            mover.left_move(ipeps, xi)
-            mover.right_move(ipeps, (ipeps.nx - xi + 1) % ipeps.nx)
+            if paired:
+                mover.left_right_move(ipeps, xi, (ipeps.nx - xi + 1) % ipeps.nx)
+            else:
+                mover.left_move(ipeps, xi)
+                mover.right_move(ipeps, (ipeps.nx - xi + 1) % ipeps.nx)
         for yi in range(ipeps.ny):
-            mover.up_move(ipeps, (ipeps.ny - yi + 1) % ipeps.ny)
-            mover.down_move(ipeps, yi)
+            if paired:
+                mover.up_down_move(ipeps, (ipeps.ny - yi + 1) % ipeps.ny, yi)
+            else:
+                mover.up_move(ipeps, (ipeps.ny - yi + 1) % ipeps.ny)
+                mover.down_move(ipeps, yi)
     return mover
