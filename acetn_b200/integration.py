@@ -1,0 +1,66 @@
+"""Drop-in installation behind the reference's own entry points.
+
+    import acetn, acetn_b200.integration as b200
+    b200.install()                                   # registers evolution.backend = "b200"
+    ipeps = acetn.ipeps.Ipeps({..., "device": "cuda", "evolution": {"backend": "b200"}})
+    ipeps.renormalize()                              # CTMRG now runs in libacetn_b200.so
+
+`install()` only touches the seams the reference itself exposes by name:
+  * `acetn.ipeps.ipeps_config.EvolutionConfig.backend` accepts "b200"; `IpepsConfig.validate_backend` RAISES (no fallback)
+    when "b200" is requested without the library or a CUDA device (the reference falls back to "torch" for "cutensor",
+    ipeps_config.py:103-109 -- the north star forbids that here);
+  * `acetn.ipeps.ipeps.ctmrg` (the name `Ipeps.renormalize` calls, ipeps.py:93-97) is wrapped: backend "b200" routes to
+    acetn_b200.renormalization.ctmrg, anything else to the untouched reference function (which stays the oracle path);
+  * `acetn.renormalization.projectors.{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}` are NOT replaced
+    globally: backend "torch" keeps the reference numerics bit for bit.
+The reference's SiteTensor / TensorNetwork objects are used as they are: the B200 mover only needs `ipeps[site]['A'|'C'|'E']`,
+`bond_permute`, `ipeps.nx/ny/dims` and writes list items in place exactly like directional_mover.py:295-303.
+"""
+import functools
+
+from . import _lib
+
+
+def install(acetn_module=None):
+    """Register backend='b200' in an importable reference package.  Returns the patched module."""
+    if acetn_module is None:
+        import acetn as acetn_module  # noqa: F401  (the reference must be importable)
+    import acetn.ipeps.ipeps as ipeps_mod
+    import acetn.ipeps.ipeps_config as cfg_mod
+    from . import renormalization as b200_renorm
+
+    if getattr(ipeps_mod, "_acetn_b200_installed", False):
+        return acetn_module
+
+    # ---- config: accept and validate the new literal -------------------------------------------------------------
+    orig_validate = cfg_mod.IpepsConfig.validate_backend
+
+    def validate_backend(self):
+        if self.evolution.backend == "b200":
+            import torch
+            if not _lib.available():
+                raise RuntimeError("backend='b200' requested but libacetn_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+            if not torch.cuda.is_available() or torch.device(self.device).type != "cuda":
+                raise RuntimeError("backend='b200' requires device='cuda' on a B200; there is no CPU fallback")
+            if self.dtype != torch.float64:
+                raise RuntimeError("backend='b200' supports dtype float64 only")
+            return
+        return orig_validate(self)
+
+    cfg_mod.IpepsConfig.validate_backend = validate_backend
+
+    # ---- CTMRG: route Ipeps.renormalize() ----------------------------------------------------------------------------
+    ref_ctmrg = ipeps_mod.ctmrg
+
+    @functools.wraps(ref_ctmrg)
+    def ctmrg(ipeps, config):
+        if getattr(ipeps.config.evolution, "backend", "torch") == "b200":
+            if getattr(ipeps, "is_distributed", False):
+                from .distributed import ShardedCtmrg
+                return ShardedCtmrg(ipeps, config, ipeps.rank, ipeps.world_size).run()
+            return b200_renorm.ctmrg(ipeps, config)
+        return ref_ctmrg(ipeps, config)
+
+    ipeps_mod.ctmrg = ctmrg
+    ipeps_mod._acetn_b200_installed = True
+    return acetn_module
