@@ -456,6 +456,10 @@ int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_s
 
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream) { return dmma_peak_launch((double*)scratch, iters, S_(stream)); }
 
+int acetn_b200_permute(double* dst, const double* src, int nd, const int64_t* dims, const int64_t* strides, void* stream) {
+    return gather_nd_launch(dst, src, nd, dims, strides, S_(stream));
+}
+
 int acetn_b200_absmax(const double* x, int64_t n, double* out, void* stream) { return absmax_launch(x, (size_t)n, out, S_(stream)); }
 int acetn_b200_frob_normalize(double* x, int64_t n, void* ws, size_t ws_bytes, void* stream) {
     if (ws_bytes < frob_scratch_doubles() * 8) { set_error("frob_normalize: workspace too small"); return ERR_WORKSPACE; }

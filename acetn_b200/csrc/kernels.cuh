@@ -15,6 +15,8 @@ size_t frob_scratch_doubles();
 int frob_normalize_launch(double* x, size_t n, double* scratch, cudaStream_t s);
 // dst (contiguous, dims d0..d4 row-major) = src[i0*s0 + ... + i4*s4]
 int gather5_launch(double* dst, const double* src, const int64_t dims[5], const int64_t strides[5], cudaStream_t s);
+// dst (contiguous over dims) = src gathered with arbitrary strides, up to 8 dims (the 'transpose' T of TTGT)
+int gather_nd_launch(double* dst, const double* src, int nd, const int64_t* dims, const int64_t* strides, cudaStream_t s);
 // dst[r*ldd + c] = src[r*lds + c] * w[c] / *div   for c < ncols   (w, div optional)
 int scale_cols_launch(double* dst, int64_t ldd, const double* src, int64_t lds, const double* w, const double* div,
                       int64_t nrows, int ncols, cudaStream_t s);

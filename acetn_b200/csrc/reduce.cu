@@ -116,6 +116,24 @@ __global__ void gather5_kernel(double* __restrict__ dst, const double* __restric
     }
 }
 
+struct GatherDims { int64_t dims[8]; int64_t strides[8]; int nd; };
+// dst (contiguous, row-major over dims[0..nd)) = src[sum_i idx_i * strides[i]]
+__global__ void gather_nd_kernel(double* __restrict__ dst, const double* __restrict__ src, GatherDims g, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        int64_t off = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            if (k < g.nd) {
+                int64_t ik = (int64_t)(r % (size_t)g.dims[k]);
+                r /= (size_t)g.dims[k];
+                off += ik * g.strides[k];
+            }
+        }
+        dst[i] = src[off];
+    }
+}
+
 __global__ void scale_cols_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
                                   const double* __restrict__ w, const double* __restrict__ div, int64_t nrows, int ncols) {
     size_t total = (size_t)nrows * ncols;
@@ -175,6 +193,17 @@ int gather5_launch(double* dst, const double* src, const int64_t dims[5], const 
     if (total == 0) return OK;
     gather5_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, src, dims[1], dims[2], dims[3], dims[4], st[0], st[1], st[2],
                                                            st[3], st[4], total);
+    AB_LAUNCHED();
+    return OK;
+}
+int gather_nd_launch(double* dst, const double* src, int nd, const int64_t* dims, const int64_t* strides, cudaStream_t s) {
+    if (nd < 1 || nd > 8) { set_error("gather_nd: 1..8 dims supported (got %d)", nd); return ERR_INVALID; }
+    GatherDims g;
+    size_t total = 1;
+    for (int i = 0; i < 8; i++) { g.dims[i] = i < nd ? dims[i] : 1; g.strides[i] = i < nd ? strides[i] : 0; if (i < nd) total *= (size_t)dims[i]; }
+    g.nd = nd;
+    if (total == 0) return OK;
+    gather_nd_kernel<<<blocks_for(total, 2), RED_THREADS, 0, s>>>(dst, src, g, total);
     AB_LAUNCHED();
     return OK;
 }

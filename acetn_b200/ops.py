@@ -250,3 +250,67 @@ def absorb_edge(ei, A_view, proj2, proj1):
                                         _p(out), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_edge")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# generic pairwise contraction (transpose-transpose-GEMM): used by the measure / norm-tensor paths
+# ---------------------------------------------------------------------------------------------------------------
+def permute_copy(view):
+    """Contiguous copy of an arbitrarily strided <= 8-d view, by the library's gather kernel."""
+    dev = _require_cuda(view)
+    out = torch.empty(view.shape, dtype=view.dtype, device=dev)
+    if out.numel() == 0:
+        return out
+    # merge nothing, just pass dims/strides (drop size-1 dims to stay within 8)
+    dims = [s for s in view.shape if s != 1] or [1]
+    strides = [st for s, st in zip(view.shape, view.stride()) if s != 1] or [1]
+    if len(dims) > 8:
+        raise RuntimeError("permute_copy: more than 8 non-trivial dims")
+    with torch.cuda.device(dev):
+        st = _lib.load().acetn_b200_permute(_p(out), _p(view), len(dims), _lib.i64_array(dims), _lib.i64_array(strides), _stream(dev))
+    _lib.check(st, "permute")
+    return out
+
+
+def _as_layout(t, labels, first, second):
+    """Return (tensor, order) with t laid out contiguously as [batch.., first.., second..] or [batch.., second.., first..]
+    without a copy when its memory already has one of the two orders; otherwise one permute copy into the first."""
+    def perm(order):
+        return t.permute([labels.index(c) for c in order])
+    for tag, order in (("fs", first[0] + first[1] + second), ("sf", first[0] + second + first[1])):
+        v = perm(order)
+        if v.is_contiguous():
+            return v, tag
+    return permute_copy(perm(first[0] + first[1] + second)), "fs"
+
+
+def contract(spec, A, B):
+    """C = einsum(spec, A, B) for a pairwise contraction, executed as (at most one gather per operand) + one batched K1
+    DGEMM.  Returns a (possibly permuted) view with the requested output leg order."""
+    lhs, out = spec.replace(" ", "").split("->")
+    sa, sb = lhs.split(",")
+    dev = _require_cuda(A, B)
+    ext = {}
+    for labels, t in ((sa, A), (sb, B)):
+        if len(labels) != t.dim():
+            raise ValueError(f"contract: spec {spec} does not match operand rank {t.dim()}")
+        for c, n in zip(labels, t.shape):
+            if ext.setdefault(c, n) != n:
+                raise ValueError(f"contract: extent mismatch on leg {c} in {spec}")
+    batch = "".join(c for c in out if c in sa and c in sb)
+    K = "".join(c for c in sa if c in sb and c not in out)
+    M = "".join(c for c in out if c in sa and c not in sb)
+    N = "".join(c for c in out if c in sb and c not in sa)
+    if set(batch + M + N) != set(out) or set(batch + M + K) != set(sa) or set(batch + K + N) != set(sb):
+        raise ValueError(f"contract: unsupported spec {spec} (traces / outer sums are not handled)")
+    prod = lambda s: int(torch.tensor([ext[c] for c in s]).prod()) if s else 1   # noqa: E731
+    nb, m, n, k = prod(batch), prod(M), prod(N), prod(K)
+    Av, ta = _as_layout(A, sa, (batch, M), K)        # [b, M, K] ("fs") or [b, K, M] ("sf")
+    Bv, tb = _as_layout(B, sb, (batch, K), N)        # [b, K, N] ("fs") or [b, N, K] ("sf")
+    C = torch.empty([ext[c] for c in batch + M + N], dtype=A.dtype, device=dev)
+    a_idx = ([0, 0, k, 0, 0, 1] if ta == "fs" else [0, 0, 1, 0, 0, m]) + [0, 0, m * k if nb > 1 else 0]
+    b_idx = ([0, 0, n, 0, 0, 1] if tb == "fs" else [0, 0, 1, 0, 0, k]) + [0, 0, k * n if nb > 1 else 0]
+    c_idx = [0, 0, n, 0, 0, 1, 0, 0, m * n if nb > 1 else 0]
+    gemm_ex(m, n, k, nb, Av, Bv, C, a_idx + b_idx + c_idx)
+    order = batch + M + N
+    return C.permute([order.index(c) for c in out])

@@ -139,6 +139,12 @@ int acetn_b200_double_layer(const double* X, int64_t n0, int64_t n1, int64_t in_
  *      caller with CUDA events it gives the live FP64 tensor-pipe roof used as the roofline denominator ---------- */
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream);
 
+/* ---- generic pairwise contraction support (measure / norm-tensor paths: rdm.py:35-154, full_update.py:209-227): the
+ *      transpose step of a transpose-transpose-GEMM-transpose contraction (what cuTENSOR's TTGT plan does in the
+ *      reference's extension, csrc/linalg/contraction.h:263).  dst is contiguous row-major over dims[0..nd);
+ *      src is read at sum_i idx_i*strides[i] (elements).  nd <= 8. */
+int acetn_b200_permute(double* dst, const double* src, int nd, const int64_t* dims, const int64_t* strides, void* stream);
+
 /* ---- small helpers used by the host shim ------------------------------------------------------------------------ */
 int acetn_b200_absmax(const double* x, int64_t n, double* out_scalar_zeroed, void* stream);
 int acetn_b200_frob_normalize(double* x, int64_t n, void* ws, size_t ws_bytes, void* stream);
