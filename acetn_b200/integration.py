@@ -62,5 +62,43 @@ def install(acetn_module=None):
         return ref_ctmrg(ipeps, config)
 
     ipeps_mod.ctmrg = ctmrg
+
+    # ---- measure: RDM contractions (measure.py:5-28 builds RDM(ipeps) and indexes it) ---------------------------------
+    import acetn.measurement.measure as meas_mod
+    from .measurement import RDM as B200RDM
+    ref_rdm = meas_mod.RDM
+
+    def rdm_factory(ipeps):
+        if getattr(ipeps.config.evolution, "backend", "torch") == "b200":
+            return B200RDM(ipeps)
+        return ref_rdm(ipeps)
+
+    meas_mod.RDM = rdm_factory
+
+    # ---- full update: norm tensor + ALS inner loop (full_update.py:54, als_solver.py:48-51) ------------------------------
+    import acetn.evolution.als_solver as als_mod
+    import acetn.evolution.full_update as fu_mod
+    from . import evolution as b200_evo
+    from . import ops as b200_ops
+    ref_norm = fu_mod.build_norm_tensor
+
+    def build_norm_tensor(ipeps, bond, a1q, a2q):
+        if getattr(ipeps.config.evolution, "backend", "torch") == "b200":
+            return b200_evo.build_norm_tensor(ipeps, bond, a1q, a2q)
+        return ref_norm(ipeps, bond, a1q, a2q)
+
+    fu_mod.build_norm_tensor = build_norm_tensor
+    ref_solve = als_mod.ALSSolver.solve
+
+    def solve(self):
+        if self.backend == "b200":
+            if self.method != "cholesky":
+                raise NotImplementedError("backend='b200': als_method must be 'cholesky'")
+            a1r, a2r, n12g = self.initialize_tensors()
+            a1r, a2r, _ = b200_ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon)
+            return a1r, a2r
+        return ref_solve(self)
+
+    als_mod.ALSSolver.solve = solve
     ipeps_mod._acetn_b200_installed = True
     return acetn_module

@@ -16,8 +16,8 @@ class RDM:
         self.ipeps = ipeps
 
     def __getitem__(self, key):
-        if len(key) == 3 and not isinstance(key[0], int):
-            return self.build_bond_rdm(key)
+        if hasattr(key, "k") or (isinstance(key, (tuple, list)) and len(key) == 3 and not isinstance(key[0], int)):
+            return self.build_bond_rdm(key)      # reference Bond dataclass (bond.py:5-22) or a plain (s1, s2, k)
         return self.build_site_rdm(key)
 
     def build_site_rdm(self, site):

@@ -314,3 +314,21 @@ def contract(spec, A, B):
     gemm_ex(m, n, k, nb, Av, Bv, C, a_idx + b_idx + c_idx)
     order = batch + M + N
     return C.permute([order.index(c) for c in out])
+
+
+def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
+    """als_solver.py:55-82 / csrc/evolution/als_solve.cpp:107-137 (cholesky method).  Returns (a1r, a2r, info) with
+    info = device int32[2] {iterations run, non-positive Cholesky pivots}."""
+    dev = _require_cuda(a1r, a2r, n12g, n12, a12g)
+    a1 = a1r.contiguous().clone()
+    a2 = a2r.contiguous().clone()
+    n12g, n12, a12g = n12g.contiguous(), n12.contiguous(), a12g.contiguous()
+    nD, bD, pD = a1.shape
+    lib = _lib.load()
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws = _ws(dev, lib.acetn_b200_als_workspace_bytes(nD, bD, pD))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_als_solve(_p(a1), _p(a2), _p(n12g), _p(n12), _p(a12g), nD, bD, pD, int(niter), float(tol), float(epsilon),
+                                      _p(info), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "als_solve")
+    return a1, a2, info

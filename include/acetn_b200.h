@@ -139,6 +139,17 @@ int acetn_b200_double_layer(const double* X, int64_t n0, int64_t n1, int64_t in_
  *      caller with CUDA events it gives the live FP64 tensor-pipe roof used as the roofline denominator ---------- */
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream);
 
+/* ---- ALS inner solver of the full update: ALSSolver.solve_torch (acetn/evolution/als_solver.py:55-82) = als_solve
+ *      of the reference's cuTENSOR extension (csrc/evolution/als_solve.cpp:107-137), cholesky method.
+ *   a1r, a2r (nD,bD,pD): in = initial guess (als_solver.py:117-146), out = result.  n12 (nD^4) [y,x,Y,X],
+ *   n12g (nD,nD,pD,pD) [Y,X,p,q], a12g (nD,nD,pD,pD) [y,x,p,q].  The whole loop (<= niter iterations, stop when the
+ *   relative cost change < tol and i > 1) runs in one cooperative kernel; info (device int32[2]) = {iterations run,
+ *   number of non-positive Cholesky pivots met (0 = clean)}. */
+size_t acetn_b200_als_workspace_bytes(int64_t nD, int64_t bD, int64_t pD);
+int acetn_b200_als_solve(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int64_t nD,
+                         int64_t bD, int64_t pD, int64_t niter, double tol, double epsilon, int32_t* info, void* ws,
+                         size_t ws_bytes, void* stream);
+
 /* ---- generic pairwise contraction support (measure / norm-tensor paths: rdm.py:35-154, full_update.py:209-227): the
  *      transpose step of a transpose-transpose-GEMM-transpose contraction (what cuTENSOR's TTGT plan does in the
  *      reference's extension, csrc/linalg/contraction.h:263).  dst is contiguous row-major over dims[0..nd);

@@ -521,3 +521,85 @@ def flops_site_move(D, chi, d=2, niter=2, p=2, chi_new=None):
 
 def flops_sweep(nx, ny, D, chi, d=2, niter=2, p=2):
     return 4 * nx * ny * flops_site_move(D, chi, d, niter, p)
+
+
+# --------------------------------------------------------------------------------------
+# full-update norm tensor and ALS inner solver (acetn/evolution/full_update.py, als_solver.py)
+# --------------------------------------------------------------------------------------
+def norm_tensor(cell: Cell, bond, a1q, a2q):
+    """full_update.py:163-227 : N12[y,x,Y,X] from the bond environment and the QR'd site tensors a1q/a2q (D,D,D,nD)."""
+    s1, s2, k = bond
+    a, b = cell[s1], cell[s2]
+    c12, e12, e11 = a.C[(k + 1) % 4], a.E[(k + 1) % 4], a.E[k % 4]
+    c13, e13 = a.C[(k + 2) % 4], a.E[(k + 2) % 4]
+    c21, e21, e24 = b.C[k % 4], b.E[k % 4], b.E[(k + 3) % 4]
+    c24, e23 = b.C[(k + 3) % 4], b.E[(k + 2) % 4]
+    t = torch.einsum("ab,bcrR->acrR", c12, e12)
+    t = torch.einsum("acrR,eauU->crReuU", t, e11)
+    t = torch.einsum("crReuU,RDUY->creuDY", t, a1q.conj())
+    t = torch.einsum("creuDY,rduy->ceDYdy", t, a1q)
+    n1 = torch.einsum("ab,bfdD->afdD", c13, e13)
+    n1 = torch.einsum("afdD,aeDYdy->feYy", n1, t)
+    t = torch.einsum("ab,bcuU->acuU", c21, e21)
+    t = torch.einsum("acuU,ealL->cuUelL", t, e24)
+    t = torch.einsum("cuUelL,DLUX->cuelXD", t, a2q.conj())
+    t = torch.einsum("cuelXD,dlux->ceXDxd", t, a2q)
+    n2 = torch.einsum("ab,fadD->bfdD", c24, e23)
+    n2 = torch.einsum("bfdD,cbXDxd->fcXx", n2, t)
+    return torch.einsum("fcYy,fcXx->yxYX", n1, n2)
+
+
+def als_cost(a1r, a2r, a12g, n12):
+    """als_solver.py:246-257."""
+    a12n = torch.einsum("yup,xuq->yxpq", a1r, a2r)
+    d2 = torch.einsum("yxYX,yxpq->YXpq", n12, a12n)
+    d2 = torch.einsum("YXpq,YXpq->", d2, a12n.conj())
+    d3 = torch.einsum("yxYX,yxpq->YXpq", n12, a12g)
+    d3 = torch.einsum("YXpq,YXpq->", d3, a12n.conj())
+    return d2.real - 2 * d3.real
+
+
+def _als_solve_ar(R, S, epsilon):
+    """als_solver.py:197-229 (cholesky branch)."""
+    nD, bD, pD = S.shape
+    S = S.reshape(nD * bD, pD)
+    R = R.reshape(nD * bD, nD * bD)
+    R = 0.5 * (R + R.mH)
+    R = R + epsilon * R.abs().max() * torch.eye(R.shape[0], dtype=R.dtype)
+    L = torch.linalg.cholesky(R)
+    Y = torch.linalg.solve_triangular(L, S, upper=False)
+    return torch.linalg.solve_triangular(L.mH, Y, upper=True).reshape(nD, bD, pD)
+
+
+def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
+    """als_solver.py:55-82 (solve_torch) = csrc/evolution/als_solve.cpp:55-105.  Returns (a1r, a2r, iterations run)."""
+    d1 = als_cost(a1r, a2r, a12g, n12).abs()
+    it = 0
+    for i in range(niter):
+        it = i + 1
+        S = torch.einsum("YXpQ,XUQ->YUp", n12g, a2r.conj())
+        R = torch.einsum("yxYX,xuq->yYXuq", n12, a2r)
+        R = torch.einsum("yYXuQ,XUQ->YUyu", R, a2r.conj())
+        a1r = _als_solve_ar(R, S, epsilon)
+        S = torch.einsum("YXPq,YVP->XVq", n12g, a1r.conj())
+        R = torch.einsum("yxYX,yvp->xYXvp", n12, a1r)
+        R = torch.einsum("xYXvP,YVP->XVxv", R, a1r.conj())
+        a2r = _als_solve_ar(R, S, epsilon)
+        d2 = als_cost(a1r, a2r, a12g, n12)
+        error = abs(d2 - d1) / d1.abs()
+        if error < tol and i > 1:
+            break
+        d1 = d2
+    return a1r, a2r, it
+
+
+def als_initial_guess(a12g, ar_shape):
+    """als_solver.py:117-146 : truncated SVD of the gate-tensor product."""
+    nD, bD, pD = ar_shape
+    m = torch.einsum("yxpq->ypxq", a12g).reshape(nD * pD, nD * pD)
+    U, S, Vh = torch.linalg.svd(m)
+    V = Vh.mH
+    S = torch.sqrt(S[:bD] / S[0])
+    a1r = torch.einsum("ypu,u->yup", U[:, :bD].reshape(nD, pD, bD), S)
+    a2r = torch.einsum("xqv,v->xvq", V[:, :bD].reshape(nD, pD, bD), S)
+    return a1r, a2r
