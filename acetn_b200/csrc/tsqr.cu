@@ -23,7 +23,8 @@ constexpr int TS_NW = TS_CH / 32;
 // Factor one chunk: P[r0:r0+rows, 0:b] = H_0 ... H_{b-1} [R; 0].  Reflectors overwrite the strictly lower part of P.
 __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
-                   double* __restrict__ tau_out) {
+                   double* __restrict__ tau_out, const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;    // second BCGS pass found the panel already orthogonal to eps
     __shared__ double v_s[TS_CH];            // current reflector (0 above its diagonal, 1 on it)
     __shared__ double part[TS_NW][TS_PB];    // per-warp partial dots
     __shared__ double partn[TS_NW];          // per-warp partial norms of the pivot column
@@ -56,7 +57,7 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
     // norm data of column 0 (later columns get theirs at the end of the previous step)
     if (c == 0) {
         double pn;
-        TS_DOT32(pn, (rbase + i > 0) ? x[i] * x[i] : 0.0);
+        if (rbase > 0) { TS_DOT32(pn, x[i] * x[i]); } else { TS_DOT32(pn, (i > 0) ? x[i] * x[i] : 0.0); }
         partn[w] = pn;
         if (w == 0) alpha_s = x[0];
     }
@@ -75,12 +76,20 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             scale = 1.0 / (alpha - beta);
         }
         if (c == j) {
+            if (rbase > j) {                     // whole slice below the pivot (warp-uniform)
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                int r = rbase + i;
-                if (r > j) { x[i] *= scale; v_s[r] = x[i]; }
-                else if (r == j) { x[i] = beta; v_s[r] = 1.0; }
-                else v_s[r] = 0.0;
+                for (int i = 0; i < 32; i++) { x[i] *= scale; v_s[rbase + i] = x[i]; }
+            } else if (rbase + 31 < j) {         // whole slice above the pivot
+#pragma unroll
+                for (int i = 0; i < 32; i++) v_s[rbase + i] = 0.0;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    int r = rbase + i;
+                    if (r > j) { x[i] *= scale; v_s[r] = x[i]; }
+                    else if (r == j) { x[i] = beta; v_s[r] = 1.0; }
+                    else v_s[r] = 0.0;
+                }
             }
             if (w == 0) tau_s[j] = tau;
         }
@@ -99,10 +108,16 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             for (int i = 0; i < 32; i++) x[i] -= v_s[rbase + i] * wc;
             if (c == j + 1) {   // norm data of the next pivot column
                 double pn;
-                TS_DOT32(pn, (rbase + i > j + 1) ? x[i] * x[i] : 0.0);
-                partn[w] = pn;
+                if (rbase > j + 1) { TS_DOT32(pn, x[i] * x[i]); }
+                else if (rbase + 31 <= j + 1) {
+                    pn = 0.0;
+                    if (rbase + 31 == j + 1) alpha_s = x[31];
+                } else {
+                    TS_DOT32(pn, (rbase + i > j + 1) ? x[i] * x[i] : 0.0);
 #pragma unroll
-                for (int i = 0; i < 32; i++) if (rbase + i == j + 1) alpha_s = x[i];
+                    for (int i = 0; i < 32; i++) if (rbase + i == j + 1) alpha_s = x[i];
+                }
+                partn[w] = pn;
             }
         }
         __syncthreads();
@@ -121,7 +136,8 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
 // Form the explicit Q rows of one chunk: Q_chunk = H_0 ... H_{b-1} [M; 0], M = Min rows [chunk*b, chunk*b + b) (identity if null).
 __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
-                  const double* __restrict__ Min) {
+                  const double* __restrict__ Min, const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;
     extern __shared__ double sm[];
     constexpr int VP = TS_CH + 1;                  // odd pitch: conflict-free column-strided stores
     double* Vs = sm;                               // [TS_PB][VP]: reflector j with unit diagonal, zeros above
@@ -169,6 +185,18 @@ tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, cons
     }
 }
 
+// run_flag = 1 iff max|c| > thresh: the re-orthogonalisation coefficients of the second BCGS pass are not negligible
+__global__ void bcgs_flag_kernel(const double* __restrict__ c, int n, double thresh, int* __restrict__ run_flag) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine |= (fabs(c[i]) > thresh) ? 1 : 0;
+    if (mine) any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) *run_flag = any;
+}
+
 namespace {
 constexpr size_t FACTOR_SMEM = 0;
 constexpr size_t APPLY_SMEM = (size_t)(TS_PB * (TS_CH + 1) + 2 * TS_NW * TS_PB + TS_PB) * sizeof(double);
@@ -197,7 +225,7 @@ size_t tsqr_scratch_doubles(int64_t m) {
 }
 
 // orthonormalise one panel P (m x b, leading dimension ld) in place
-int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, cudaStream_t s) {
+int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, const int* run_flag, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
@@ -213,12 +241,12 @@ int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, cudaStr
         mat[l + 1] = rst[l]; lds[l + 1] = b;
     }
     for (int l = 0; l < L.n; l++) {
-        tsqr_factor_kernel<<<(unsigned)L.chunks[l], TS_CH, FACTOR_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, rst[l], tau[l]);
+        tsqr_factor_kernel<<<(unsigned)L.chunks[l], TS_CH, FACTOR_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, rst[l], tau[l], run_flag);
         AB_LAUNCHED();
     }
     for (int l = L.n - 1; l >= 0; l--) {
         const double* Min = (l == L.n - 1) ? nullptr : mat[l + 1];
-        tsqr_apply_kernel<<<(unsigned)L.chunks[l], TS_CH, APPLY_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, tau[l], Min);
+        tsqr_apply_kernel<<<(unsigned)L.chunks[l], TS_CH, APPLY_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, tau[l], Min, run_flag);
         AB_LAUNCHED();
     }
     return OK;
@@ -236,7 +264,7 @@ GemmDesc proj_update_desc(double* Y, int64_t ld, int64_t m, int j0, int b, const
 
 size_t orthonormalize_workspace_bytes(int64_t m, int q) {
     size_t bytes = ws_round(tsqr_scratch_doubles(m) * sizeof(double));
-    bytes += ws_round((size_t)q * TS_PB * sizeof(double));
+    bytes += ws_round((size_t)q * TS_PB * sizeof(double)) + ws_round(16 * sizeof(int));
     size_t g = 0;
     for (int j0 = TS_PB; j0 < q; j0 += TS_PB) {
         int b = (q - j0) < TS_PB ? (q - j0) : TS_PB;
@@ -254,6 +282,7 @@ int orthonormalize_launch(double* Y, int64_t m, int q, int64_t ld, void* wsp, si
     Workspace ws(wsp, ws_bytes);
     double* scratch = ws.take<double>(tsqr_scratch_doubles(m));
     double* Sc = ws.take<double>((size_t)q * TS_PB);
+    int* flag = ws.take<int>(16);
     if (ws.overflow) { set_error("orthonormalize: workspace too small"); return ERR_WORKSPACE; }
     void* gws = ws.base + ws.used;
     size_t gws_bytes = ws.bytes - ws.used;
@@ -261,11 +290,19 @@ int orthonormalize_launch(double* Y, int64_t m, int q, int64_t ld, void* wsp, si
         int b = (q - j0) < TS_PB ? (q - j0) : TS_PB;
         for (int pass = 0; pass < 2; pass++) {
             if (j0 == 0 && pass == 1) break;   // the first panel has nothing to be re-orthogonalised against
+            const int* run_flag = nullptr;
             if (j0 > 0) {
                 AB_TRY(gemm_launch(proj_coeff_desc(Y, ld, m, j0, b, Sc), gws, gws_bytes, s));
+                if (pass == 1) {
+                    // "twice is enough": if the second-pass coefficients are below 1e-10 the panel is orthonormal to
+                    // O(1e-20 * j0*b) after the update and the second TSQR is skipped on the device (no host sync)
+                    bcgs_flag_kernel<<<1, 256, 0, s>>>(Sc, j0 * b, 1e-10, flag);
+                    AB_LAUNCHED();
+                    run_flag = flag;
+                }
                 AB_TRY(gemm_launch(proj_update_desc(Y, ld, m, j0, b, Sc), gws, gws_bytes, s));
             }
-            AB_TRY(tsqr_panel(Y + j0, m, b, ld, scratch, s));
+            AB_TRY(tsqr_panel(Y + j0, m, b, ld, scratch, run_flag, s));
         }
     }
     return OK;
