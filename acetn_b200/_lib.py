@@ -30,14 +30,14 @@ SIGNATURES = {
     "acetn_b200_quarter_tensor": (c_int, [c_vp, c_vp, c_vp, c_vp, P_i64] + [c_i64] * 6 + [c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_rsvd_workspace_bytes": (c_sz, [c_int, P_i64, P_i64, c_i64]),
     "acetn_b200_rsvd": (c_int, [c_int, ctypes.POINTER(c_vp), P_i64, P_i64, c_vp, c_i64, c_int, c_int, c_i64, c_dbl,
-                                c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_orthonormalize_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "acetn_b200_orthonormalize": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "acetn_b200_jacobi_svd_workspace_bytes": (c_sz, [c_i64]),
     "acetn_b200_jacobi_svd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_projectors_workspace_bytes": (c_sz, [c_i64] * 5),
     "acetn_b200_projectors_from_usv": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
-                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                               c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_absorb_corner_workspace_bytes": (c_sz, [c_i64] * 5),
     "acetn_b200_absorb_corner1": (c_int, [c_vp, c_vp, c_vp] + [c_i64] * 5 + [c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_absorb_corner2": (c_int, [c_vp, c_vp, c_vp] + [c_i64] * 5 + [c_vp, c_vp, c_sz, c_vp]),

@@ -269,7 +269,7 @@ size_t acetn_b200_rsvd_workspace_bytes(int nmat, const int64_t* rows, const int6
 
 int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, const int64_t* cols, const double* Omega, int64_t q,
                     int niter, int reorth_adjoint, int64_t chi, double cutoff, double* U, double* S, double* V, int32_t* info,
-                    void* wsp, size_t ws_bytes, void* stream) {
+                    double* AtQ, double* Wt_out, void* wsp, size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     AB_REQUIRE(nmat >= 1 && nmat <= 4, "rsvd: nmat must be 1..4");
     Chain c; c.n = nmat;
@@ -300,13 +300,23 @@ int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, co
         AB_TRY(chain_apply(c, false, Z, Y, t0, t1, q, g, gb, s));                 // Y = (M0..Mn-1) Z
     }
     AB_TRY(orthonormalize_launch(Y, m, (int)q, q, g, gb, s));                      // Q
-    AB_TRY(chain_apply(c, true, Y, Z, t0, t1, q, g, gb, s));                      // Z = Bt^T  (n x q),  Bt = Q^H M
+    if (AtQ != nullptr && c.n >= 2) {
+        // keep M0^T Q (the first product of the adjoint chain): proj1 = M0^T U = (M0^T Q) U_B needs no further pass over M0
+        AB_TRY(gemm_launch(thin_desc(c.mat[0], c.rows[0], c.cols[0], true, Y, AtQ, q), g, gb, s));
+        Chain rest; rest.n = c.n - 1;
+        for (int i = 1; i < c.n; i++) { rest.mat[i - 1] = c.mat[i]; rest.rows[i - 1] = c.rows[i]; rest.cols[i - 1] = c.cols[i]; }
+        AB_TRY(chain_apply(rest, true, AtQ, Z, t0, t1, q, g, gb, s));
+    } else {
+        AB_TRY(chain_apply(c, true, Y, Z, t0, t1, q, g, gb, s));                  // Z = Bt^T  (n x q),  Bt = Q^H M
+        if (AtQ != nullptr) AB_CHECK_CUDA(cudaMemcpyAsync(AtQ, Z, (size_t)(n * q) * 8, cudaMemcpyDeviceToDevice, s));
+    }
     AB_CHECK_CUDA(cudaMemcpyAsync(Qb, Z, (size_t)(n * q) * 8, cudaMemcpyDeviceToDevice, s));
     AB_TRY(orthonormalize_launch(Qb, n, (int)q, q, g, gb, s));                     // Bt^T = Qb R
     AB_TRY(gemm_launch(core_desc(Qb, Z, n, q, R), g, gb, s));                     // R = Qb^T Bt^T   (q x q)
     AB_TRY(jacobi_svd_launch(R, (int)q, S, Wt, Jt, (int)chi, cutoff, (int*)info, g, gb, s));   // R = Jt^T S Wt
-    AB_TRY(gemm_launch(lift_desc(Y, m, q, Wt, U), g, gb, s));                     // U = Q  Wt^T
+    if (U != nullptr) AB_TRY(gemm_launch(lift_desc(Y, m, q, Wt, U), g, gb, s));   // U = Q  Wt^T
     AB_TRY(gemm_launch(lift_desc(Qb, n, q, Jt, V), g, gb, s));                    // V = Qb Jt^T
+    if (Wt_out != nullptr) AB_CHECK_CUDA(cudaMemcpyAsync(Wt_out, Wt, (size_t)(q * q) * 8, cudaMemcpyDeviceToDevice, s));
     return OK;
 }
 
@@ -320,28 +330,45 @@ GemmDesc p2_desc(const double* Q4, int64_t m4, int64_t n4, const double* Vs, int
 }
 }  // namespace
 size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep) {
-    size_t b = ws_round((size_t)(m1 * keep) * 8) + ws_round((size_t)(n4 * keep) * 8) + ws_round((size_t)keep * 8);
+    const int64_t qmax = m1 < n4 ? m1 : n4;          // q <= min(m, n)
+    size_t b = ws_round((size_t)(m1 * keep) * 8) + ws_round((size_t)(n4 * keep) * 8) + ws_round((size_t)keep * 8) +
+               2 * ws_round((size_t)(qmax * keep) * 8);
     size_t g = maxz(gemm_workspace_bytes(p1_desc(nullptr, m1, n1, nullptr, keep, nullptr)),
                     gemm_workspace_bytes(p2_desc(nullptr, m4, n4, nullptr, keep, nullptr)));
     return b + g + 4096;
 }
 int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
                                    const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S, int64_t keep,
-                                   const double* qmax1, const double* qmax4, double* proj1, double* proj2, void* wsp,
-                                   size_t ws_bytes, void* stream) {
+                                   const double* qmax1, const double* qmax4, const double* AtQ, const double* Wt, int64_t q,
+                                   double* proj1, double* proj2, void* wsp, size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     AB_REQUIRE(keep >= 1, "projectors: keep must be >= 1");
+    AB_REQUIRE((AtQ == nullptr) == (Wt == nullptr), "projectors: AtQ and Wt must be given together");
     Workspace ws(wsp, ws_bytes);
     double* Us = ws.take<double>((size_t)(m1 * keep));
     double* Vs = ws.take<double>((size_t)(n4 * keep));
     double* w = ws.take<double>((size_t)keep);
+    const int64_t qcap = m1 < n4 ? m1 : n4;
+    double* Ub = ws.take<double>((size_t)(qcap * keep));
+    double* Ubs = ws.take<double>((size_t)(qcap * keep));
     if (ws.overflow) { set_error("projectors: workspace too small"); return ERR_WORKSPACE; }
+    AB_REQUIRE(AtQ == nullptr || q <= qcap, "projectors: q exceeds min(m1, n4)");
     void* g = ws.base + ws.used;
     size_t gb = ws.bytes - ws.used;
     AB_TRY(inv_sqrt_weights_launch(S, w, (int)keep, s));
-    AB_TRY(scale_cols_launch(Us, keep, U, ldu, w, qmax1, m1, (int)keep, s));
     AB_TRY(scale_cols_launch(Vs, keep, V, ldv, w, qmax4, n4, (int)keep, s));
-    AB_TRY(gemm_launch(p1_desc(Q1, m1, n1, Us, keep, proj1), g, gb, s));
+    if (AtQ != nullptr) {
+        // proj1 = (Q1^T Qy) (U_B diag(w)) : Us <- Wt^T[:, :keep] * w / qmax1  (q x keep), one small GEMM instead of a pass over Q1
+        int64_t dims[5] = {q, keep, 1, 1, 1};
+        int64_t st[5] = {1, q, 0, 0, 0};
+        AB_TRY(gather5_launch(Ub, Wt, dims, st, s));
+        AB_TRY(scale_cols_launch(Ubs, keep, Ub, keep, w, qmax1, q, (int)keep, s));
+        AB_TRY(gemm_launch(gemm_desc((int)n1, (int)keep, (int)q, operand(AtQ, idx1(q), idx1(1)), operand(Ubs, idx1(keep), idx1(1)), proj1,
+                                     idx1(keep), idx1(1)), g, gb, s));
+    } else {
+        AB_TRY(scale_cols_launch(Us, keep, U, ldu, w, qmax1, m1, (int)keep, s));
+        AB_TRY(gemm_launch(p1_desc(Q1, m1, n1, Us, keep, proj1), g, gb, s));
+    }
     AB_TRY(gemm_launch(p2_desc(Q4, m4, n4, Vs, keep, proj2), g, gb, s));
     return OK;
 }

@@ -10,9 +10,8 @@
 
 namespace ab200 {
 
-constexpr int BK = 16;
-constexpr int STAGES = 4;
-constexpr int PADK = BK + 4;   // row length (doubles) of a k-contiguous smem tile
+constexpr int BK_DEFAULT = 16;
+// BK = 16 -> 4 stages, BK = 32 -> 3 stages (shared-memory budget); k-contiguous smem rows are padded by 4 doubles
 
 struct GemmKernelParams {
     int M, N, K, batch, splitk, tiles_n, tiles_mn, kt_total;
@@ -25,8 +24,10 @@ struct GemmKernelParams {
     int fast;            // both k indices single-level and both operands vectorisable: pointer-increment loader
 };
 
-template <int BM, int BN, bool A_MC, bool B_KC>
+template <int BM, int BN, bool A_MC, bool B_KC, int BK>
 struct SmemLayout {
+    static constexpr int STAGES = BK == 16 ? 4 : 3;
+    static constexpr int PADK = BK + 4;
     static constexpr int A_LD = A_MC ? (BM + 4) : PADK;
     static constexpr int A_ROWS = A_MC ? BK : BM;
     static constexpr int B_LD = B_KC ? PADK : (BN + 4);
@@ -47,10 +48,11 @@ struct TileLoader {
     static constexpr int PER_THREAD = (CHUNKS + NT - 1) / NT;
 };
 
-template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC>
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC, int BK>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
 dgemm_dmma_kernel(const GemmKernelParams p) {
-    using L = SmemLayout<BM, BN, A_MC, B_KC>;
+    using L = SmemLayout<BM, BN, A_MC, B_KC, BK>;
+    constexpr int STAGES = L::STAGES;
     constexpr int NWARP_N = BN / WN;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
@@ -260,21 +262,23 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
         const uint32_t sB_n = sA_n + (uint32_t)(L::A_ELEMS * 8);
         const int64_t ao = (int64_t)nxt * a_kstep, bo = (int64_t)nxt * b_kstep;
 
-        const double* As = smem + (size_t)(it % STAGES) * L::STAGE_ELEMS;
-        const double* Bs = As + L::A_ELEMS;
+        // fragments are fetched with volatile ld.shared one k-step ahead of the DMMAs that consume them (explicit
+        // register double buffering: ptxas would otherwise sink the loads next to their use and expose LDS latency)
+        const uint32_t sA_c = smem_base + (uint32_t)((it % STAGES) * L::STAGE_ELEMS * 8);
+        const uint32_t sB_c = sA_c + (uint32_t)(L::A_ELEMS * 8);
         double af[2][MT], bf[2][NTL];
 #pragma unroll
-        for (int i = 0; i < MT; i++) af[0][i] = As[a_off[i]];
+        for (int i = 0; i < MT; i++) af[0][i] = lds_f64(sA_c + (uint32_t)(a_off[i] * 8));
 #pragma unroll
-        for (int j = 0; j < NTL; j++) bf[0][j] = Bs[b_off[j]];
+        for (int j = 0; j < NTL; j++) bf[0][j] = lds_f64(sB_c + (uint32_t)(b_off[j] * 8));
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; kk++) {
             const int cur = kk & 1, nx = cur ^ 1;
             if (kk + 1 < KSTEPS) {
 #pragma unroll
-                for (int i = 0; i < MT; i++) af[nx][i] = As[a_off[i] + (kk + 1) * A_KSTRIDE];
+                for (int i = 0; i < MT; i++) af[nx][i] = lds_f64(sA_c + (uint32_t)((a_off[i] + (kk + 1) * A_KSTRIDE) * 8));
 #pragma unroll
-                for (int j = 0; j < NTL; j++) bf[nx][j] = Bs[b_off[j] + (kk + 1) * B_KSTRIDE];
+                for (int j = 0; j < NTL; j++) bf[nx][j] = lds_f64(sB_c + (uint32_t)((b_off[j] + (kk + 1) * B_KSTRIDE) * 8));
             }
 #pragma unroll
             for (int j = 0; j < NTL; j++) {
@@ -369,7 +373,8 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int M, int N
 namespace {
 
 struct Plan {
-    int tile;        // 1: 128x128 (16 warps), 2: 128x88, 3: 64x64, 4: 128x128 (8 warps, 32x64 warp tiles), 5: 64x88 (4 warps)
+    int bk;
+    int tile;        // 1: 128x128 (16 warps), 2: 128x88, 3: 64x64, 4: 128x128 (8 warps, 32x64 warp tiles), 5: 64x88 (4 warps), 6: 128x88 BK=32, 7: 64x64 BK=32
     int bm, bn;
     int splitk;
     bool a_mc, b_kc;
@@ -400,16 +405,17 @@ Plan make_plan(const GemmDesc& d) {
         long long tiles = (long long)((d.M + bm - 1) / bm) * ((d.N + bn - 1) / bn) * d.batch * splitk;
         long long waves = (tiles + sms - 1) / sms;
         // time ~ waves * tile_area * K/splitk  (+ fixed per-CTA overhead of ~6 k-tiles)
-        double kt = (double)((d.K + BK - 1) / BK) / splitk + 6.0;
+        double kt = (double)((d.K + 15) / 16) / splitk + 6.0;
         double t = (double)waves * bm * bn * kt;
         if (splitk > 1) t += 3.0 * (double)d.M * d.N * d.batch * splitk / sms * 2.0;   // partial write + reduce traffic
         return t;
     };
-    int tiles_opt[5][2] = {{128, 128}, {128, 88}, {64, 64}, {128, 128}, {64, 88}};
+    int tiles_opt[7][2] = {{128, 128}, {128, 88}, {64, 64}, {128, 128}, {64, 88}, {128, 88}, {64, 64}};
+    int bk_opt[7] = {16, 16, 16, 16, 16, 32, 32};
     double best = 1e300;
-    pl.tile = 1; pl.bm = 128; pl.bn = 128; pl.splitk = 1;
-    const int kt_total = (d.K + BK - 1) / BK;
-    for (int t = 0; t < 5; t++) {
+    pl.tile = 1; pl.bm = 128; pl.bn = 128; pl.splitk = 1; pl.bk = 16;
+    const int kt_total = (d.K + 15) / 16;
+    for (int t = 0; t < 7; t++) {
         if (d.force_tile && d.force_tile != t + 1) continue;
         if (!d.force_tile && t >= 3) continue;   // tiles 4,5 only on request until measured
         int bm = tiles_opt[t][0], bn = tiles_opt[t][1];
@@ -418,18 +424,18 @@ Plan make_plan(const GemmDesc& d) {
             if (s > 1 && kt_total / s < 8) break;
             double c = waves_cost(bm, bn, s);
             if (t == 0) c *= 1.15;   // measured: 128x128 (16 warps, 128 regs) 28 TF vs 64x64 (3 CTAs/SM) 32 TF on square shapes
-            if (c < best) { best = c; pl.tile = t + 1; pl.bm = bm; pl.bn = bn; pl.splitk = s; }
+            if (c < best) { best = c; pl.tile = t + 1; pl.bm = bm; pl.bn = bn; pl.splitk = s; pl.bk = bk_opt[t]; }
         }
     }
     if (d.force_splitk) pl.splitk = d.force_splitk;
     return pl;
 }
 
-template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC>
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC, int BK>
 int launch_cfg(const GemmKernelParams& kp, cudaStream_t stream) {
-    using L = SmemLayout<BM, BN, A_MC, B_KC>;
+    using L = SmemLayout<BM, BN, A_MC, B_KC, BK>;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_KC>;
+    auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_KC, BK>;
     static bool configured = false;
     if (!configured) {
         AB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
@@ -445,12 +451,12 @@ int launch_cfg(const GemmKernelParams& kp, cudaStream_t stream) {
     return OK;
 }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int BK = BK_DEFAULT>
 int launch_orient(const GemmKernelParams& kp, bool a_mc, bool b_kc, cudaStream_t stream) {
-    if (!a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, false, false>(kp, stream);
-    if (a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, true, false>(kp, stream);
-    if (!a_mc && b_kc) return launch_cfg<BM, BN, WM, WN, false, true>(kp, stream);
-    return launch_cfg<BM, BN, WM, WN, true, true>(kp, stream);
+    if (!a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, false, false, BK>(kp, stream);
+    if (a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, true, false, BK>(kp, stream);
+    if (!a_mc && b_kc) return launch_cfg<BM, BN, WM, WN, false, true, BK>(kp, stream);
+    return launch_cfg<BM, BN, WM, WN, true, true, BK>(kp, stream);
 }
 
 }  // namespace
@@ -470,7 +476,7 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     memset(&kp, 0, sizeof(kp));
     kp.M = d.M; kp.N = d.N; kp.K = d.K; kp.batch = d.batch; kp.splitk = pl.splitk;
     kp.tiles_n = (d.N + pl.bn - 1) / pl.bn;
-    kp.kt_total = (d.K + BK - 1) / BK;
+    kp.kt_total = (d.K + pl.bk - 1) / pl.bk;
     kp.A = d.A; kp.B = d.B; kp.C = d.C; kp.cm = d.cm; kp.cn = d.cn; kp.cb = d.cb;
     kp.alpha = d.alpha; kp.beta = d.beta;
     kp.a_vec = pl.a_vec; kp.b_vec = pl.b_vec;
@@ -489,6 +495,8 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     else if (pl.tile == 2) st = launch_orient<128, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
     else if (pl.tile == 4) st = launch_orient<128, 128, 32, 64>(kp, pl.a_mc, pl.b_kc, stream);
     else if (pl.tile == 5) st = launch_orient<64, 88, 16, 88>(kp, pl.a_mc, pl.b_kc, stream);
+    else if (pl.tile == 6) st = launch_orient<128, 88, 16, 88, 32>(kp, pl.a_mc, pl.b_kc, stream);
+    else if (pl.tile == 7) st = launch_orient<64, 64, 32, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     else st = launch_orient<64, 64, 32, 32>(kp, pl.a_mc, pl.b_kc, stream);
     if (st) return st;
     if (pl.splitk > 1) {

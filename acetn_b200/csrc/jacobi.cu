@@ -42,11 +42,13 @@ __device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja
         sab += __shfl_xor_sync(0xffffffffu, sab, o);
     }
     if (saa == 0.0 || sbb == 0.0) return 0.0;
-    double rel = fabs(sab) / sqrt(saa * sbb);
-    if (rel <= tol) return rel;
+    // relative criterion |xa.xb| <= tol |xa||xb| tested without sqrt/div; the ratio is only formed for pairs that rotate
+    const double r2 = sab * sab, den = saa * sbb;
+    if (r2 <= tol * tol * den) return 0.0;
+    const double rel = sqrt(r2 / den);
     double zeta = (sbb - saa) / (2.0 * sab);
     double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+    double cs = rsqrt(1.0 + t * t), sn = cs * t;
     for (int c = lane; c < ncols; c += 32) {
         double u = xa[c], v = xb[c];
         xa[c] = cs * u - sn * v;

@@ -149,9 +149,11 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     return S, Wt, Jt, info
 
 
-def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None):
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False):
     """Randomized SVD of mats[0] @ ... @ mats[-1] with the caller's test matrix omega (n, q).
-    Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps])."""
+    Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps]).
+    want_atq=True additionally returns (AtQ, Wt) = (mats[0]^T Q, core left vectors as rows) and want_u=False skips U
+    (then U is None): the half-system projector pipeline needs only AtQ, Wt and V."""
     dev = _require_cuda(*mats, omega)
     mats = [m.contiguous() for m in mats]
     omega = omega.contiguous()
@@ -163,26 +165,31 @@ def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, str
         raise ValueError("rsvd: omega rows must equal the column count of the last factor")
     m = rows[0]
     lib = _lib.load()
-    U = torch.empty(m, q, dtype=torch.float64, device=dev)
+    U = torch.empty(m, q, dtype=torch.float64, device=dev) if want_u else None
     S = torch.empty(q, dtype=torch.float64, device=dev)
     V = torch.empty(n, q, dtype=torch.float64, device=dev)
-    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    AtQ = torch.empty(cols[0], q, dtype=torch.float64, device=dev) if want_atq else None
+    Wt = torch.empty(q, q, dtype=torch.float64, device=dev) if want_atq else None
+    info = torch.empty(2, dtype=torch.int32, device=dev)      # written by the library (no torch kernel on another stream)
     r_arr, c_arr = _lib.i64_array(rows), _lib.i64_array(cols)
     nb = lib.acetn_b200_rsvd_workspace_bytes(nmat, r_arr, c_arr, q)
     ws = _ws(dev, nb, stream)
     ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() for t in mats])
     with torch.cuda.device(dev):
         st = lib.acetn_b200_rsvd(nmat, ptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
-                                 q if chi is None else int(chi), float(cutoff), _p(U), _p(S), _p(V), _p(info), _p(ws), ws.numel(),
+                                 q if chi is None else int(chi), float(cutoff), _p(U) if want_u else None, _p(S), _p(V), _p(info),
+                                 _p(AtQ) if want_atq else None, _p(Wt) if want_atq else None, _p(ws), ws.numel(),
                                  _stream(dev, stream))
     _lib.check(st, "rsvd")
+    if want_atq:
+        return U, S, V, info, AtQ, Wt
     return U, S, V, info
 
 
-def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=None):
+def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=None, AtQ=None, Wt=None):
     """projectors.py:166-173. Q1 (m1,n1), Q4 (m4,n4), U (m1,q), V (n4,q). Returns proj1 (n1,keep), proj2 (m4,keep).
     qmax1/qmax4: max|Q| scalars of un-normalised Q1/Q4 (see acetn_b200.h)."""
-    dev = _require_cuda(Q1, Q4, U, V, S)
+    dev = _require_cuda(Q1, Q4, V, S)
     m1, n1 = Q1.shape
     m4, n4 = Q4.shape
     lib = _lib.load()
@@ -191,8 +198,11 @@ def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=No
     nb = lib.acetn_b200_projectors_workspace_bytes(m1, n1, m4, n4, keep)
     ws = _ws(dev, nb, stream)
     with torch.cuda.device(dev):
-        st = lib.acetn_b200_projectors_from_usv(_p(Q1), m1, n1, _p(Q4), m4, n4, _p(U), U.stride(0), _p(V), V.stride(0), _p(S), keep,
+        st = lib.acetn_b200_projectors_from_usv(_p(Q1), m1, n1, _p(Q4), m4, n4, _p(U) if U is not None else None,
+                                                U.stride(0) if U is not None else 0, _p(V), V.stride(0), _p(S), keep,
                                                 _p(qmax1) if qmax1 is not None else None, _p(qmax4) if qmax4 is not None else None,
+                                                _p(AtQ) if AtQ is not None else None, _p(Wt) if Wt is not None else None,
+                                                Wt.shape[0] if Wt is not None else 0,
                                                 _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev, stream))
     _lib.check(st, "projectors_from_usv")
     return p1, p2

@@ -68,10 +68,11 @@ class ProjectorCalculator:
         mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
         Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=stream, absmax=mx[0:1])
         Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=stream, absmax=mx[1:2])
-        U, S, V, info = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi, cutoff=self.svd_cutoff,
-                                 stream=stream)
-        return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": U, "S": S, "V": V, "info": info, "omega": omega,
-                "stream": stream}
+        # U is never materialised: proj1 = Q1^T U = (Q1^T Qy) U_B reuses the first product of the final adjoint pass
+        _, S, V, info, AtQ, Wt = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi,
+                                          cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True)
+        return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": None, "S": S, "V": V, "info": info,
+                "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream}
 
     def begin_full_system(self, ipeps, sites, k, stream=None, omega=None):
         """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
@@ -120,8 +121,8 @@ class ProjectorCalculator:
         q1D, q4D = pend["q1D"], pend["q4D"]
         if pend["kind"] == "half":
             mx = pend["mx"]
-            p1, p2 = ops.projectors_from_usv(pend["Q1"], pend["Q4"], pend["U"], pend["V"], S, keep, stream=stream,
-                                             qmax1=mx[0:1], qmax4=mx[1:2])
+            p1, p2 = ops.projectors_from_usv(pend["Q1"], pend["Q4"], None, pend["V"], S, keep, stream=stream,
+                                             qmax1=mx[0:1], qmax4=mx[1:2], AtQ=pend["AtQ"], Wt=pend["Wt"])
         else:
             # projectors.py:209-217 : proj1 = Q1^H (Q2^H conj(U)), proj2 = Q4 (Q3 V), columns scaled by s^-1/2
             # (runs on the main stream; finish() already synchronised the side stream)

@@ -77,11 +77,14 @@ int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E
  *   reorth_adjoint != 0 re-orthonormalises between the adjoint and forward halves of each power step
  *   (fused_3matmul_svd_lowrank.py:39-45).
  *   Outputs: U (rows[0] x q), S (q, descending), V (cols[nmat-1] x q)  [V not transposed, as the reference],
- *   info (device int32[2]): info[0] = min(chi, #{S/S[0] > cutoff})  (projectors.py:163-164), info[1] = Jacobi sweeps. */
+ *   info (device int32[2]): info[0] = min(chi, #{S/S[0] > cutoff})  (projectors.py:163-164), info[1] = Jacobi sweeps.
+ *   Optional (may be NULL): U may be NULL when only AtQ/Wt are wanted; AtQ (cols[0] x q) receives M_0^T Q, the first
+ *   product of the final adjoint pass, and Wt (q x q) the left singular vectors of the core as rows (U = Q Wt^T), so that
+ *   proj1 = M_0^T conj(U) = AtQ Wt^T can be formed without another pass over M_0 (see projectors_from_usv). */
 size_t acetn_b200_rsvd_workspace_bytes(int nmat, const int64_t* rows, const int64_t* cols, int64_t q);
 int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, const int64_t* cols, const double* Omega,
                     int64_t q, int niter, int reorth_adjoint, int64_t chi, double cutoff, double* U, double* S,
-                    double* V, int32_t* info, void* ws, size_t ws_bytes, void* stream);
+                    double* V, int32_t* info, double* AtQ, double* Wt, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- orthonormal basis of a tall matrix (torch.linalg.qr(Y).Q, fused_matmul_svd_lowrank.py:38,43), in place */
 size_t acetn_b200_orthonormalize_workspace_bytes(int64_t m, int64_t q);
@@ -98,12 +101,15 @@ int acetn_b200_jacobi_svd(const double* R, int64_t q, double* S, double* Wt, dou
  *   proj1 out: n1 x keep, proj2 out: m4 x keep.
  *   qmax1 / qmax4 (device doubles, may be NULL): when Q1 / Q4 were produced with normalize = 0, passing their max|Q|
  *   here divides proj1 / proj2 by it, which reproduces the reference's normalised-Q projectors exactly while saving the
- *   two HBM passes of the division over the 2 GiB tensors. */
+ *   two HBM passes of the division over the 2 GiB tensors.
+ *   AtQ (n1 x q) and Wt (q x q) from acetn_b200_rsvd (may both be NULL): when given, proj1 = AtQ (Wt^T diag(w)) is formed
+ *   by one small GEMM and Q1 / U are not read (saves 2 m1 n1 keep flop = one of the 14 large GEMMs of a site-move). */
 size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep);
 int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
                                    const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S,
-                                   int64_t keep, const double* qmax1, const double* qmax4, double* proj1, double* proj2,
-                                   void* ws, size_t ws_bytes, void* stream);
+                                   int64_t keep, const double* qmax1, const double* qmax4, const double* AtQ,
+                                   const double* Wt, int64_t q, double* proj1, double* proj2, void* ws, size_t ws_bytes,
+                                   void* stream);
 
 /* ---- absorption: DirectionalMover.renormalize_cj1/cj2/ej, acetn/renormalization/directional_mover.py:306-366 ---
  *   corner1: out[a,x] = sum ei[a,b,l,L] ci[b,c] proj[c,l,L,x] / ||.||     ci (chi_b,chi_c) ei (chi_a,chi_b,D,D) proj (chi_c,D,D,chi_x)
