@@ -124,7 +124,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 16.0 * t_move * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"CTMRG sweep, D={args.D} chi={args.chi} d={args.d}, 2x2 cell, half-system rsvd niter=2 p=2", "device": "cpu"},
+            "config": {"workload": f"CTMRG sweep, D={args.D} chi={args.chi} d={args.d}, {'2x2' if args.gpus <= 1 else '4x4'} cell "
+                                   f"({16 if args.gpus <= 1 else 64} site-moves/sweep), half-system rsvd niter=2 p=2",
+                       "value_unit": "sweeps of 16 site-moves per second", "device": "cpu (reference torch path, oracle port)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
