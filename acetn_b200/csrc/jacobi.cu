@@ -14,7 +14,7 @@ namespace cg = cooperative_groups;
 
 namespace ab200 {
 
-constexpr int JB_THREADS = 512;   // 16 warps: one warp per row pair of a local step
+constexpr int JB_THREADS = 256;   // 8 warps: one warp per row pair of a local step (br <= 8)
 
 struct JacobiParams {
     double* X;      // n x ld, row major (n = nb * br rows, zero padded)
@@ -28,12 +28,15 @@ struct JacobiParams {
     int* info;      // [0] sweeps used
 };
 
-// Rotate rows (xa, xb) of X (and ja, jb of J) held in shared memory so that xa . xb = 0.  One warp.
-__device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja, double* jb, int ncols, double tol, int lane) {
+// Rotate rows (xa, xb) of X (and ja, jb of J) held in shared memory so that xa . xb = 0.  One warp; rows are read
+// as double2 (the row pitch is even and the pad column, if any, is zero in X and J).
+__device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja, double* jb, int ncols2, double tol, int lane) {
+    double2* xa2 = reinterpret_cast<double2*>(xa);
+    double2* xb2 = reinterpret_cast<double2*>(xb);
     double saa = 0.0, sbb = 0.0, sab = 0.0;
-    for (int c = lane; c < ncols; c += 32) {
-        double u = xa[c], v = xb[c];
-        saa += u * u; sbb += v * v; sab += u * v;
+    for (int c = lane; c < ncols2; c += 32) {
+        double2 u = xa2[c], v = xb2[c];
+        saa += u.x * u.x + u.y * u.y; sbb += v.x * v.x + v.y * v.y; sab += u.x * v.x + u.y * v.y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -49,13 +52,15 @@ __device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja
     double zeta = (sbb - saa) / (2.0 * sab);
     double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     double cs = rsqrt(1.0 + t * t), sn = cs * t;
-    for (int c = lane; c < ncols; c += 32) {
-        double u = xa[c], v = xb[c];
-        xa[c] = cs * u - sn * v;
-        xb[c] = sn * u + cs * v;
-        double ju = ja[c], jv = jb[c];
-        ja[c] = cs * ju - sn * jv;
-        jb[c] = sn * ju + cs * jv;
+    double2* ja2 = reinterpret_cast<double2*>(ja);
+    double2* jb2 = reinterpret_cast<double2*>(jb);
+    for (int c = lane; c < ncols2; c += 32) {
+        double2 u = xa2[c], v = xb2[c], r;
+        r.x = cs * u.x - sn * v.x; r.y = cs * u.y - sn * v.y; xa2[c] = r;
+        r.x = sn * u.x + cs * v.x; r.y = sn * u.y + cs * v.y; xb2[c] = r;
+        double2 ju = ja2[c], jv = jb2[c];
+        r.x = cs * ju.x - sn * jv.x; r.y = cs * ju.y - sn * jv.y; ja2[c] = r;
+        r.x = sn * ju.x + cs * jv.x; r.y = sn * ju.y + cs * jv.y; jb2[c] = r;
     }
     return rel;
 }
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int br = p.br, nb = p.nb, ld = p.ld, ncols = p.ncols;
+    const int br = p.br, nb = p.nb, ld = p.ld, ncols2 = p.ld / 2;
     const int npairs = nb / 2, nbm1 = nb - 1;
     double* Xs = sm;                       // [2*br][ld]
     double* Js = sm + (size_t)2 * br * ld;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
                             if (i == 0) { a = brm1; b = t; }
                             else { a = (t + i) % brm1; b = (t - i + brm1) % brm1; }
                             a += blk * br; b += blk * br;
-                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols, p.tol, lane);
+                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, lane);
                             worst = fmax(worst, rel);
                         }
                         __syncthreads();
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
                     for (int t = 0; t < br; t++) {
                         if (warp < br) {
                             int a = warp, b = br + (warp + t) % br;
-                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols, p.tol, lane);
+                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, lane);
                             worst = fmax(worst, rel);
                         }
                         __syncthreads();
@@ -197,7 +202,7 @@ struct JacobiGeom { int br, nb, n, ld; size_t smem; };
 JacobiGeom jacobi_geom(int q) {
     JacobiGeom g;
     g.ld = q + (q & 1);                                  // even row pitch: 16-byte staging copies
-    g.br = 16;
+    g.br = 8;                                            // 8-row blocks: more CTAs (FP64 throughput of the active SMs is the limiter), 2 warps/SMSP
     while (g.br > 2 && (size_t)4 * g.br * g.ld * sizeof(double) > 220 * 1024) g.br /= 2;
     g.nb = (q + g.br - 1) / g.br;
     if (g.nb & 1) g.nb++;

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
                    double* __restrict__ tau_out, const int* __restrict__ run_flag) {
     if (run_flag != nullptr && *run_flag == 0) return;    // second BCGS pass found the panel already orthogonal to eps
-    __shared__ double v_s[TS_CH];            // current reflector (0 above its diagonal, 1 on it)
+    __shared__ __align__(16) double v_s[TS_CH];   // current reflector (0 above its diagonal, 1 on it)
     __shared__ double part[TS_NW][TS_PB];    // per-warp partial dots
     __shared__ double partn[TS_NW];          // per-warp partial norms of the pivot column
     __shared__ double alpha_s;
@@ -95,8 +95,14 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
         }
         __syncthreads();
         // ---- apply H_j to the trailing columns
+        double vv[32];
+        {
+            const double2* v2 = reinterpret_cast<const double2*>(v_s + rbase);
+#pragma unroll
+            for (int i = 0; i < 16; i++) { double2 t = v2[i]; vv[2 * i] = t.x; vv[2 * i + 1] = t.y; }
+        }
         double dsum;
-        TS_DOT32(dsum, v_s[rbase + i] * x[i]);
+        TS_DOT32(dsum, vv[i] * x[i]);
         part[w][c] = dsum;
         __syncthreads();
         if (c > j && c < b) {
@@ -105,7 +111,7 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             for (int k = 0; k < TS_NW; k++) wc += part[k][c];
             wc *= tau;
 #pragma unroll
-            for (int i = 0; i < 32; i++) x[i] -= v_s[rbase + i] * wc;
+            for (int i = 0; i < 32; i++) x[i] -= vv[i] * wc;
             if (c == j + 1) {   // norm data of the next pivot column
                 double pn;
                 if (rbase > j + 1) { TS_DOT32(pn, x[i] * x[i]); }
@@ -139,7 +145,7 @@ tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, cons
                   const double* __restrict__ Min, const int* __restrict__ run_flag) {
     if (run_flag != nullptr && *run_flag == 0) return;
     extern __shared__ double sm[];
-    constexpr int VP = TS_CH + 1;                  // odd pitch: conflict-free column-strided stores
+    constexpr int VP = TS_CH + 2;                  // even pitch: 16-byte aligned rows for LDS.128 reads of the reflectors
     double* Vs = sm;                               // [TS_PB][VP]: reflector j with unit diagonal, zeros above
     double* part = sm + TS_PB * VP;             // [2][TS_NW][TS_PB]
     double* tau_s = part + 2 * TS_NW * TS_PB;      // [TS_PB]
@@ -164,7 +170,10 @@ tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, cons
 
     int buf = 0;
     for (int j = nref - 1; j >= 0; j--) {
-        const double* v = Vs + j * VP + rbase;
+        const double2* v2 = reinterpret_cast<const double2*>(Vs + j * VP + rbase);
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { double2 t = v2[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
         double dsum;
         TS_DOT32(dsum, v[i] * z[i]);
         double* pb = part + buf * TS_NW * TS_PB;
@@ -199,7 +208,7 @@ __global__ void bcgs_flag_kernel(const double* __restrict__ c, int n, double thr
 
 namespace {
 constexpr size_t FACTOR_SMEM = 0;
-constexpr size_t APPLY_SMEM = (size_t)(TS_PB * (TS_CH + 1) + 2 * TS_NW * TS_PB + TS_PB) * sizeof(double);
+constexpr size_t APPLY_SMEM = (size_t)(TS_PB * (TS_CH + 2) + 2 * TS_NW * TS_PB + TS_PB) * sizeof(double);
 
 struct Levels {
     int n;

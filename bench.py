@@ -106,6 +106,34 @@ def cpu_site_move_seconds(args, reps=1):
     return best
 
 
+def gpu_torch_site_move_seconds(args, dev):
+    """The reference's torch path (oracle port: torch.einsum / @ / linalg.qr / linalg.svd -> cuBLAS + cuSOLVER) on the SAME
+    GPU: the comparator BASELINE.md asks for besides the CPU baseline.  One site-move, best of 2 after one warm-up."""
+    import torch
+    from oracle import ctmrg_oracle as orc
+    cell = orc.random_cell(2, 2, args.D, args.chi, args.d, seed=args.seed)
+    for s in cell.site_list:
+        st = cell[s]
+        st.A = st.A.to(dev)
+        st.C = [c.to(dev) for c in st.C]
+        st.E = [e.to(dev) for e in st.E]
+    cfg = orc.CtmrgConfig()
+    omega_fn = lambda n, q, dtype=torch.float64, device=dev: torch.randn(n, q, dtype=dtype, device=dev)   # noqa: E731
+    best = 1e30
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p1, p2 = orc.half_system_projectors(cell, orc.plaquette(cell, 0, 0, 0), 0, cfg, omega_fn=omega_fn)
+        work = cell.clone()
+        orc.renormalize_boundary(work, {0: p1, 1: p1}, {0: p2, 1: p2}, (0, 0), (1, 0), 0, 1, 0)
+        torch.cuda.synchronize()
+        if it > 0:
+            best = min(best, time.perf_counter() - t0)
+        del p1, p2, work
+    torch.cuda.empty_cache()
+    return best
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU torch path (oracle port), one bounded sample (= one site-move) per step."""
     import torch
@@ -295,6 +323,14 @@ def run_b200(args):
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if n == 1 and not args.no_cpu_baseline:
+            try:
+                t_gpu = gpu_torch_site_move_seconds(args, dev)
+                line["gpu_torch_baseline"] = {"value": 1.0 / (16.0 * t_gpu), "unit": UNIT, "kind": "port",
+                                              "sample": f"one site-move of the reference torch path (cuBLAS/cuSOLVER via torch) on this GPU, "
+                                                        f"{t_gpu * 1e3:.1f} ms, scaled x16 to a 2x2 sweep"}
+            except Exception as ex:   # noqa: BLE001  (baseline only; never affects the measured arm)
+                line["gpu_torch_baseline"] = {"unavailable": str(ex)[:200]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
