@@ -90,7 +90,9 @@ def assert_same_shapes(ref, got):
 
 # ------------------------------------------------------------------------------------------------ synchronized moves
 SYNC_CASES = [("random", 2, 8, 2, 0, 2, 2), ("random", 3, 12, 2, 1, 2, 2), ("random", 2, 6, 2, 3, 3, 2), ("random", 4, 16, 2, 5, 2, 2),
-              ("random", 3, 9, 3, 6, 2, 2), ("product", 3, 18, 2, 7, 2, 2)]
+              ("random", 3, 9, 3, 6, 2, 2), ("product", 3, 18, 2, 7, 2, 2),
+              ("random", 4, 64, 2, 8, 2, 2),      # BASELINE config 2 shape (TFIM D=4 chi=64)
+              ("random", 2, 20, 2, 9, 2, 2)]      # BASELINE config 1 shape (README quickstart D=2 chi=20)
 
 
 @pytest.mark.parametrize("kind,D,chi,d,seed,nx,ny", SYNC_CASES)
@@ -201,6 +203,33 @@ def test_free_running_within_reference_envelope(case):
     # the first move starts from identical states and must agree to the tight tolerance
     ny = cell.ny
     assert spectra_err(s_ref[:ny], s_got[:ny], cell.dims["chi"]) < 1e-10
+
+
+@pytest.mark.parametrize("D,chi,d", [(6, 36, 2), (8, 24, 2), (7, 14, 4)])
+def test_single_move_larger_bond_dimension(D, chi, d):
+    """One synchronized left move at the bond dimensions of BASELINE configs 3-5 (D=6, 8, 7 with d=4) at a chi the CPU
+    oracle finishes in seconds: exercises the fused K2 (D=8), odd-D scalar loaders (D=7) and d>2."""
+    cell = orc.random_cell(2, 2, D, chi, d, seed=11)
+    torch.manual_seed(3)
+    ip = Ipeps.from_plain(cell, CTMRGConfig())
+    mover = DirectionalMover(ip.ctmrg_config)
+    mover.projector_calculator.spectra = []
+    tape, rec = orc.OmegaTape(), {}
+    orc.directional_move(cell, 0, 0, orc.CtmrgConfig(), tape, rec)
+    linalg.set_omega_source(orc.OmegaTape(tape.tape))
+    try:
+        mover.left_move(ip, 0)
+    finally:
+        linalg.set_omega_source(None)
+    got = to_oracle_cell(ip)
+    assert_same_shapes(cell, got)
+    assert spectra_err(rec["spectra"], mover.projector_calculator.spectra, chi) < 1e-10
+    for y in range(2):
+        for k in (0, 3):
+            a, b = torch.linalg.svdvals(got[(1, y)].C[k]), torch.linalg.svdvals(cell[(1, y)].C[k])
+            assert float((a / a[0] - b / b[0]).abs().max()) < 1e-9
+    r0, r1 = orc.site_rdm(cell, (1, 0)), orc.site_rdm(got, (1, 0))
+    assert float((r0 / r0.trace() - r1 / r1.trace()).abs().max()) < 1e-9
 
 
 def test_projector_pi_invariant():
