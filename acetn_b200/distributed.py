@@ -80,6 +80,8 @@ def phase_moves(ipeps):
 
 class ShardedCtmrg:
     def __init__(self, ipeps, config, rank, world, compute=None, group=None):
+        if getattr(config, "svd_type", "rsvd") != "rsvd":
+            raise ValueError("site-sharded CTMRG supports svd_type='rsvd' only")
         if config.projectors != "half-system":
             raise ValueError("site-sharded CTMRG needs half-system projectors (full-system moves of a pair are not independent, "
                              "SURVEY.md App. D4)")

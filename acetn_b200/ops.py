@@ -326,6 +326,16 @@ def contract(spec, A, B):
     return C.permute([order.index(c) for c in out])
 
 
+def absmax(x, out):
+    """out[0] = max(out[0], max|x|)  (out: 1-element device tensor, zero it first)."""
+    dev = _require_cuda(x, out)
+    x = x.contiguous()
+    with torch.cuda.device(dev):
+        st = _lib.load().acetn_b200_absmax(_p(x), x.numel(), _p(out), _stream(dev))
+    _lib.check(st, "absmax")
+    return out
+
+
 def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
     """als_solver.py:55-82 / csrc/evolution/als_solve.cpp:107-137 (cholesky method).  Returns (a1r, a2r, info) with
     info = device int32[2] {iterations run, non-positive Cholesky pivots}."""

@@ -51,15 +51,71 @@ class ProjectorCalculator:
         return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax)
 
     def _check_svd_type(self):
-        if self.svd_type == "full-rank":
-            raise NotImplementedError("backend='b200': svd_type='full-rank' is not implemented (use 'rsvd')")
-        if self.svd_type != "rsvd":
+        if self.svd_type not in ("rsvd", "full-rank"):
             raise ValueError(f"Invalid svd_type: {self.svd_type} provided.")
+
+    # ---- svd_type == "full-rank" (projectors.py:114-136, 138-142, 176-179) ------------------------------------------
+    FULL_RANK_MAX = 3400      # size limit of the block-Jacobi core (shared-memory staging of row-block pairs)
+
+    @staticmethod
+    def full_svd(M):
+        """torch.linalg.svd(M) (projectors.py:229-231) from the same kernels as the randomized path: M = Qb Rc (K4 + one
+        K1 product), Rc = Jt^T diag(S) Wt (K5)  =>  U = Qb Jt^T, V = Wt^T.  Returns U (m,n), S (n) descending, V (n,n)."""
+        m, n = M.shape
+        if m < n or n > ProjectorCalculator.FULL_RANK_MAX:
+            raise NotImplementedError(f"backend='b200': svd_type='full-rank' supports m >= n <= {ProjectorCalculator.FULL_RANK_MAX} "
+                                      f"(got {m}x{n}); use svd_type='rsvd'")
+        Qb = ops.orthonormalize(M.clone())
+        Rc = ops.matmul(Qb, M, transpose_a=True)                  # (n, n)
+        S, Wt, Jt, info = ops.jacobi_svd(Rc)
+        U = ops.matmul(Qb, Jt.t().contiguous())
+        return U, S, Wt.t().contiguous()
+
+    def _full_rank_projectors(self, R1, R2, F, d1, d4, chi):
+        """calculate_projectors (projectors.py:114-136) for explicitly formed R1 (m, .), R2 (., n) and F = R1 R2."""
+        U, S, V = self.full_svd(F)
+        s = S / S[0]
+        keep = min(chi, int((s > self.svd_cutoff).sum().item()))
+        if self.spectra is not None:
+            self.spectra.append(s.detach().cpu())
+        w = 1.0 / torch.sqrt(s[:keep])
+        Us = (U[:, :keep] * w).contiguous()
+        Vs = (V[:, :keep] * w).contiguous()
+        p1 = ops.matmul(R1, Us, transpose_a=True)                 # einsum("xedD,xz->edDz", R1, conj(U))
+        p2 = ops.matmul(R2, Vs)                                   # einsum("cuUy,yz->cuUz", R2, V)
+        return p1.view(*d1[3:], keep), p2.view(*d4[:3], keep)
+
+    @staticmethod
+    def _normalized(M):
+        mx = torch.zeros(1, dtype=M.dtype, device=M.device)
+        ops.absmax(M, mx)
+        return M / mx
+
+    def _full_rank_half_system(self, ipeps, sites, k):
+        """contract_half_system + calculate_projectors (projectors.py:62-82, 138-142)."""
+        Q1, d1 = self.make_quarter_tensor(ipeps[sites[0]], k)
+        Q4, d4 = self.make_quarter_tensor(ipeps[sites[3]], k + 3)
+        R = self._normalized(ops.matmul(Q1, Q4))
+        return self._full_rank_projectors(Q1, Q4, R, d1, d4, ipeps.dims["chi"])
+
+    def _full_rank_full_system(self, ipeps, sites, k):
+        """contract_full_system + calculate_projectors (projectors.py:84-112, 176-179)."""
+        s1, s2, s3, s4 = sites
+        Q1, d1 = self.make_quarter_tensor(ipeps[s1], k)
+        Q2, _ = self.make_quarter_tensor(ipeps[s2], k + 1)
+        Q3, _ = self.make_quarter_tensor(ipeps[s3], k + 2)
+        Q4, d4 = self.make_quarter_tensor(ipeps[s4], k + 3)
+        R1 = self._normalized(ops.matmul(Q2, Q1))
+        R2 = self._normalized(ops.matmul(Q4, Q3))
+        F = self._normalized(ops.matmul(R1, R2))
+        return self._full_rank_projectors(R1, R2, F, d1, d4, ipeps.dims["chi"])
 
     # ---- phase 1 ------------------------------------------------------------------------------------------------
     def begin_half_system(self, ipeps, sites, k, stream=None, omega=None):
         """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed)."""
         self._check_svd_type()
+        if self.svd_type == "full-rank":
+            return {"kind": "done", "result": self._full_rank_half_system(ipeps, sites, k), "stream": None}
         s1, s4 = sites[0], sites[3]
         st1, st4 = ipeps[s1], ipeps[s4]
         chi = ipeps.dims["chi"]
@@ -77,6 +133,8 @@ class ProjectorCalculator:
     def begin_full_system(self, ipeps, sites, k, stream=None, omega=None):
         """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
         self._check_svd_type()
+        if self.svd_type == "full-rank":
+            return {"kind": "done", "result": self._full_rank_full_system(ipeps, sites, k), "stream": None}
         s1, s2, s3, s4 = sites
         chi = ipeps.dims["chi"]
         if omega is None:
@@ -95,6 +153,9 @@ class ProjectorCalculator:
         (torch.randn(n, q) on the tensors' device, fused_matmul_svd_lowrank.py:32): one draw per projector, in call order."""
         chi = ipeps.dims["chi"]
         D = ipeps.dims["bond"]
+        if self.svd_type == "full-rank":
+            ipeps[sites[0]], ipeps[sites[3]]      # same ValueError on unknown sites; no random draw in this mode
+            return None
         if self.projectors == "half-system":
             st1, st4 = ipeps[sites[0]], ipeps[sites[3]]
             m = st1['E'][(0 + k) % 4].shape[1] * D * D            # rows of Q1: chi_c of E[k]
@@ -111,6 +172,8 @@ class ProjectorCalculator:
 
     # ---- phase 2 ------------------------------------------------------------------------------------------------
     def finish(self, pend):
+        if pend["kind"] == "done":
+            return pend["result"]
         stream = pend["stream"]
         if stream is not None:
             stream.synchronize()

@@ -232,6 +232,29 @@ def test_single_move_larger_bond_dimension(D, chi, d):
     assert float((r0 / r0.trace() - r1 / r1.trace()).abs().max()) < 1e-9
 
 
+@pytest.mark.parametrize("projectors", ["half-system", "full-system"])
+def test_full_rank_svd_type(projectors):
+    """svd_type='full-rank' (projectors.py:114-136): deterministic (no Omega); one sweep against the oracle."""
+    cell = orc.random_cell(2, 2, 2, 8, 2, seed=12)
+    ocfg = orc.CtmrgConfig(steps=1, projectors=projectors, svd_type="full-rank")
+    ref = cell.clone()
+    rec = {}
+    orc.directional_move(ref, 0, 0, ocfg, record=rec)
+    ip = Ipeps.from_plain(cell, CTMRGConfig(steps=1, projectors=projectors, svd_type="full-rank"))
+    mover = DirectionalMover(ip.ctmrg_config)
+    mover.projector_calculator.spectra = []
+    mover.left_move(ip, 0)
+    got = to_oracle_cell(ip)
+    assert_same_shapes(ref, got)
+    for a, b in zip(rec["spectra"], mover.projector_calculator.spectra):
+        assert float((a - b)[:8].abs().max()) < 1e-10
+    assert abs(energy(got) - energy(ref)) < 1e-9
+    U, S, V = ProjectorCalculator.full_svd(torch.randn(60, 40, dtype=torch.float64, generator=torch.Generator().manual_seed(1)).cuda())
+    assert U.shape == (60, 40) and V.shape == (40, 40)
+    with pytest.raises(ValueError):
+        ProjectorCalculator(CTMRGConfig(svd_type="bogus")).calculate(ip, [(0, 0), (1, 0), (1, 1), (0, 1)], 0)
+
+
 def test_projector_pi_invariant():
     """Pi = proj2 proj1^T is gauge invariant; compare with the oracle on the same Omega."""
     cell = orc.random_cell(2, 2, 3, 12, 2, seed=1)
