@@ -304,7 +304,10 @@ def run_b200(args):
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "kernel": "dgemm_dmma_kernel (K1), thin GEMM %dx%dx%d" % (m, q, m),
                     "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 entry)",
-                    "whole_sweep_tflops": orc.flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n}
+                    "whole_sweep_tflops": orc.flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n,
+                    # 13 thin DGEMMs per site-move (12 rSVD + proj2), per rank; share = their summed duration / step time
+                    "launches_per_step": 13 * site_moves // n,
+                    "share_of_step": (13 * site_moves / n) * t_gemm / (ms * 1e-3 / args.steps)}
         del Q, X
         ops.release_workspace()
         torch.cuda.empty_cache()
