@@ -25,10 +25,19 @@ import torch
 import torch.distributed as dist
 
 
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class B200Compute:
     """Default backend: libacetn_b200.so through acetn_b200.renormalization."""
 
     def __init__(self, config):
+        self.config = config
         from .renormalization import DirectionalMover
         self.mover = DirectionalMover(config)
         self.pc = self.mover.projector_calculator
@@ -39,8 +48,9 @@ class B200Compute:
     def draw_omega(self, ipeps, task):
         return self.pc.draw_omega(ipeps, task["plaq"], task["k"])
 
-    def projectors(self, ipeps, tasks, omegas):
-        """Projector pairs of the given (owned) tasks -> list of (proj1, proj2)."""
+    def projectors(self, ipeps, tasks, omegas, group=None, group_rank=0, group_size=1):
+        """Projector pairs of the given tasks -> list of (proj1, proj2).  With group_size > 1 every task is computed
+        cooperatively by the ranks of `group` (row-sharded quarter tensors and rSVD products, sharded_projector.py)."""
         if not tasks:
             return []
         device = ipeps[tasks[0]["s1"]]['A'].device
@@ -49,8 +59,23 @@ class B200Compute:
         for st in streams:
             if st is not None:
                 st.wait_stream(main)
-        pend = [self.pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n]) for n, t in enumerate(tasks)]
-        out = [self.pc.finish(pd) for pd in pend]
+        if group_size <= 1:
+            pend = [self.pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n]) for n, t in enumerate(tasks)]
+            out = [self.pc.finish(pd) for pd in pend]
+        else:
+            from .sharded_projector import ShardedHalfSystemProjector
+            sp = ShardedHalfSystemProjector(self.mover.projector_calculator, group, group_rank, group_size)
+            sp.cfg = self.config
+            sp.spectra = self.pc.spectra
+            ctx = [torch.cuda.stream(streams[n % len(streams)]) if streams[0] is not None else _Null() for n in range(len(tasks))]
+            pend = []
+            for n, t in enumerate(tasks):
+                with ctx[n]:
+                    pend.append(sp.begin(ipeps, t["plaq"], t["k"], omegas[n]))
+            out = []
+            for n, pd in enumerate(pend):
+                with (torch.cuda.stream(streams[n % len(streams)]) if streams[0] is not None else _Null()):
+                    out.append(sp.finish(pd))
         for st in streams:
             if st is not None:
                 main.wait_stream(st)
@@ -79,7 +104,10 @@ def phase_moves(ipeps):
 
 
 class ShardedCtmrg:
-    def __init__(self, ipeps, config, rank, world, compute=None, group=None):
+    """group_size G > 1: ranks [iG, (i+1)G) form a group that computes each of its projector tasks cooperatively
+    (row-sharded, see sharded_projector.py); tasks are dealt to the world/G groups, absorptions to single ranks."""
+
+    def __init__(self, ipeps, config, rank, world, compute=None, group=None, group_size=1):
         if getattr(config, "svd_type", "rsvd") != "rsvd":
             raise ValueError("site-sharded CTMRG supports svd_type='rsvd' only")
         if config.projectors != "half-system":
@@ -88,6 +116,17 @@ class ShardedCtmrg:
         self.ipeps, self.config, self.rank, self.world, self.group = ipeps, config, rank, world, group
         self.compute = compute if compute is not None else B200Compute(config)
         self.bytes_exchanged = 0
+        if group_size < 1 or world % group_size != 0:
+            raise ValueError(f"group_size {group_size} must divide the world size {world}")
+        self.G = group_size
+        self.ngroups = world // group_size
+        self.gi, self.g = rank // group_size, rank % group_size
+        self.pair_group = None
+        if group_size > 1:
+            for i in range(self.ngroups):         # every rank creates every group (torch.distributed requirement)
+                pg = dist.new_group(ranks=list(range(i * group_size, (i + 1) * group_size)))
+                if i == self.gi:
+                    self.pair_group = pg
 
     # ---- helpers ---------------------------------------------------------------------------------------------------
     def _bcast(self, tensor, src):
@@ -96,8 +135,12 @@ class ShardedCtmrg:
             self.bytes_exchanged += tensor.numel() * tensor.element_size()
         return tensor
 
+    def owner_group(self, n):
+        return n % self.ngroups
+
     def owner(self, n):
-        return n % self.world
+        """Rank that broadcasts the projector pair of task n and runs its absorptions."""
+        return self.owner_group(n) * self.G + (n // self.ngroups) % self.G
 
     # ---- one phase ---------------------------------------------------------------------------------------------------
     def phase(self, moves):
@@ -106,8 +149,14 @@ class ShardedCtmrg:
         for k, line in moves:
             tasks += cp.tasks(ip, k, line)
         omegas = [cp.draw_omega(ip, t) for t in tasks]                    # every rank replays every draw
-        mine = [n for n in range(len(tasks)) if self.owner(n) == rank]
-        pairs = cp.projectors(ip, [tasks[n] for n in mine], [omegas[n] for n in mine])
+        coop = [n for n in range(len(tasks)) if self.owner_group(n) == self.gi]      # tasks my group computes
+        if self.G > 1:
+            coop_pairs = cp.projectors(ip, [tasks[n] for n in coop], [omegas[n] for n in coop], group=self.pair_group,
+                                       group_rank=self.g, group_size=self.G)
+        else:
+            coop_pairs = cp.projectors(ip, [tasks[n] for n in coop], [omegas[n] for n in coop])
+        mine = [n for n in coop if self.owner(n) == rank]
+        pairs = [pr for n, pr in zip(coop, coop_pairs) if self.owner(n) == rank]
         A0 = ip[tasks[0]["s1"]]['A']
         device, dtype = A0.device, A0.dtype
         D = ip.dims["bond"]

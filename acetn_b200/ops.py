@@ -27,7 +27,8 @@ def _require_cuda(*tensors):
 
 def _ws(dev, nbytes, stream=None):
     """Per-(device, stream) grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
-    sid = 0 if stream is None else stream.cuda_stream
+    # one scratch buffer per CUDA stream: work enqueued on different streams may run concurrently
+    sid = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), sid)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -77,8 +78,9 @@ def gemm_ex(M, N, K, batch, A, B, C, idx, alpha=1.0, beta=0.0, force_tile=0, for
     return C
 
 
-def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0):
-    """C = op(A) @ B for 2-D row-major tensors through K1 (test/bench convenience)."""
+def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0, out=None):
+    """C = op(A) @ B for 2-D row-major tensors through K1.  out: optional contiguous (M, N) destination (e.g. a row block
+    of a larger row-major matrix)."""
     A = A.contiguous()
     B = B.contiguous()
     if transpose_a:
@@ -88,7 +90,12 @@ def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0):
         M, K = A.shape
         a_idx = [0, 0, K, 0, 0, 1, 0, 0, 0]
     N = B.shape[1]
-    C = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    if out is None:
+        C = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    else:
+        if tuple(out.shape) != (M, N) or not out.is_contiguous():
+            raise ValueError("matmul: out must be a contiguous (M, N) tensor")
+        C = out
     idx = a_idx + [0, 0, N, 0, 0, 1, 0, 0, 0] + [0, 0, N, 0, 0, 1, 0, 0, 0]
     return gemm_ex(M, N, K, 1, A, B, C, idx, force_tile=force_tile, force_splitk=force_splitk)
 

@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--group-size", type=int, default=0, help="ranks cooperating on one projector (0 = auto)")
     return ap.parse_args()
 
 
@@ -179,6 +180,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = max(world, 1)
+    gsz = 1
     nx = args.nx or (2 if n == 1 else 4)
     ny = args.ny or (2 if n == 1 else 4)
     D, chi, d = args.D, args.chi, args.d
@@ -191,7 +193,8 @@ def run_b200(args):
 
     if world > 1:
         from acetn_b200.distributed import ShardedCtmrg
-        sharded = ShardedCtmrg(ip, cfg, rank, world)
+        gsz = args.group_size or (2 if world >= 8 else 1)
+        sharded = ShardedCtmrg(ip, cfg, rank, world, group_size=gsz)
         sweep = sharded.sweep
     else:
         def sweep():
@@ -320,7 +323,7 @@ def run_b200(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"CTMRG sweep, D={D} chi={chi} d={d}, {nx}x{ny} cell ({site_moves} site-moves/sweep), half-system rsvd niter=2 p=2",
-                           "cell": f"{nx}x{ny}", "value_unit": "sweeps of 16 site-moves per second", "parallelism": f"site-sharded x{n}",
+                           "cell": f"{nx}x{ny}", "value_unit": "sweeps of 16 site-moves per second", "parallelism": f"site-sharded x{n}" + (f", {gsz} ranks per projector (row-sharded)" if n > 1 and gsz > 1 else ""),
                            "l2": "inputs (2 GiB quarter tensors) exceed the 126 MB L2; no flush between iterations"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}

@@ -29,10 +29,16 @@ class OracleCompute:
         m = cell[task["plaq"][0]].E[k % 4].shape[1] * D * D
         return self.tape(n, min(chi + self.cfg.rsvd_oversampling, m, n))
 
-    def projectors(self, cell, tasks, omegas):
+    def projectors(self, cell, tasks, omegas, group=None, group_rank=0, group_size=1):
         out = []
-        for t, om in zip(tasks, omegas):
-            out.append(orc.half_system_projectors(cell, t["plaq"], t["k"], self.cfg, omega_fn=lambda n, q, dt=None, dv=None, om=om: om))
+        if group_size > 1:
+            from acetn_b200.sharded_projector import ShardedHalfSystemProjector
+            sp = ShardedHalfSystemProjector(self.cfg, group, group_rank, group_size, la=TorchLinAlg())
+            pend = [sp.begin(cell, t["plaq"], t["k"], om) for t, om in zip(tasks, omegas)]
+            out = [sp.finish(pd) for pd in pend]
+        else:
+            for t, om in zip(tasks, omegas):
+                out.append(orc.half_system_projectors(cell, t["plaq"], t["k"], self.cfg, omega_fn=lambda n, q, dt=None, dv=None, om=om: om))
         return [(a.contiguous(), b.contiguous()) for a, b in out]
 
     def absorb(self, cell, task, p1i, p2i, p1j, p2j):
@@ -50,7 +56,7 @@ def _max_diff(a, b):
     return err
 
 
-def _worker(rank, world, port, nx, ny, kind, ret):
+def _worker(rank, world, port, nx, ny, kind, ret, group_size=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
@@ -63,9 +69,11 @@ def _worker(rank, world, port, nx, ny, kind, ret):
         ref = cell.clone()
         tape = orc.OmegaTape()
         orc.ctmrg(ref, cfg, omega_fn=tape)
-        sh = ShardedCtmrg(cell, cfg, rank, world, compute=OracleCompute(cfg, orc.OmegaTape(tape.tape)))
+        sh = ShardedCtmrg(cell, cfg, rank, world, compute=OracleCompute(cfg, orc.OmegaTape(tape.tape)), group_size=group_size)
         sh.run()
-        ret[rank] = (_max_diff(ref, cell), sh.bytes_exchanged)
+        H = orc.heisenberg_bond_hamiltonian(1.0)
+        de = abs(float(orc.measure(ref, H)["Energy"]) - float(orc.measure(cell, H)["Energy"]))
+        ret[rank] = (_max_diff(ref, cell) if group_size == 1 else de, sh.bytes_exchanged)
     finally:
         dist.destroy_process_group()
 
@@ -82,6 +90,22 @@ def test_sharded_schedule_gloo_world2(nx, ny, kind):
         err, nbytes = ret[rank]
         assert err == 0.0, f"rank {rank}: sharded sweep differs from the sequential oracle sweep by {err}"
         assert nbytes > 0
+
+
+def test_group_cooperative_schedule_gloo_world2():
+    """world 2, group_size 2: both ranks compute every projector cooperatively (row-sharded), absorptions alternate.
+    Product-state start (well conditioned): the energy after two sweeps equals the sequential oracle's to 1e-9."""
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 2, 2, "product", ret, 2), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        de, nbytes = ret[rank]
+        assert de < 1e-9, de
+        assert nbytes > 0
+    assert ret[0][0] == ret[1][0]
 
 
 def test_sharded_schedule_single_rank_equals_sequential():
@@ -112,3 +136,88 @@ def test_move_tasks_match_oracle_pickers():
                 mine = DirectionalMover.move_tasks(cell, k, line)
                 ref = orc.move_tasks(cell, k, line)
                 assert [(t["key"], t["plaq"], t["s1"], t["s2"], t["i"], t["j"]) for t in mine] == [tuple(r) for r in ref]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row-sharded projector (acetn_b200/sharded_projector.py) on gloo with a torch linear-algebra backend
+# ---------------------------------------------------------------------------------------------------------------------
+class TorchLinAlg:
+    """Test-only backend of ShardedHalfSystemProjector: the exchange logic is what is under test here."""
+
+    def quarter_rows(self, site, k, c0, c1, absmax):
+        sl = orc.Site(site.A, list(site.C), list(site.E))
+        sl.E[k % 4] = site.E[k % 4][:, c0:c1]
+        ak = sl.bond_permute(k)
+        t = torch.einsum("ab,bcuU->acuU", sl.C[k % 4], sl.E[k % 4])
+        t = torch.einsum("acuU,ealL->cuUelL", t, sl.E[(3 + k) % 4])
+        t = torch.einsum("cuUelL,LURDP->cuelRDP", t, ak.conj())
+        t = torch.einsum("lurdp,cuelRDp->crRedD", ak, t)
+        shp = t.shape
+        Q = t.reshape(shp[0] * shp[1] * shp[2], shp[3] * shp[4] * shp[5])
+        if Q.numel():
+            absmax[0] = max(float(absmax[0]), float(Q.abs().max()))
+        return Q
+
+    def matmul(self, A, B, transpose_a=False, out=None):
+        r = (A.T if transpose_a else A) @ B
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def orthonormalize(self, Y):
+        Y.copy_(torch.linalg.qr(Y).Q)
+        return Y
+
+    def core_svd(self, R, chi, cutoff):
+        U, S, Vh = torch.linalg.svd(R)          # R = U S Vh  =>  Jt = U^T, Wt = Vh
+        keep = min(chi, int((S / S[0] > cutoff).sum()))
+        return S, Vh.contiguous(), U.T.contiguous(), torch.tensor([keep, 0])
+
+    def keep_of(self, info):
+        return int(info[0])
+
+
+def _proj_worker(rank, world, port, kind, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from acetn_b200.sharded_projector import ShardedHalfSystemProjector
+        cfg = orc.CtmrgConfig()
+        if kind == "random":
+            cell = orc.random_cell(2, 2, 3, 7, 2, seed=4)       # chi = 7: uneven row blocks
+        else:
+            cell = orc.product_cell(2, 2, 2, 10, 2, seed=2)
+            orc.ctmrg(cell, orc.CtmrgConfig(steps=1))             # ragged chi legs
+        plaq = orc.plaquette(cell, 0, 0, 0)
+        tape, rec = orc.OmegaTape(), {}
+        p1r, p2r = orc.half_system_projectors(cell, plaq, 0, cfg, omega_fn=tape, record=rec)
+        sp = ShardedHalfSystemProjector(cfg, None, rank, world, la=TorchLinAlg())
+        sp.spectra = []
+        p1, p2 = sp.finish(sp.begin(cell, plaq, 0, tape.tape[0]))
+        chi = cell.dims["chi"]
+        ds = float((rec["spectra"][0] - sp.spectra[0])[:chi].abs().max())
+        m = p1r.shape[0] * p1r.shape[1] * p1r.shape[2]
+        pi_ref = p2r.reshape(m, -1) @ p1r.reshape(m, -1).T
+        pi = p2.reshape(m, -1) @ p1.reshape(m, -1).T
+        ret[rank] = (tuple(p1.shape) == tuple(p1r.shape), ds, float((pi - pi_ref).norm() / pi_ref.norm()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["random", "product"])
+def test_row_sharded_projector_gloo_world2(kind):
+    world = 2
+    port = 31500 + (os.getpid() % 2000) + (3 if kind == "random" else 5)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_proj_worker, args=(world, port, kind, ret), nprocs=world, join=True)
+    for rank in range(world):
+        same_shape, ds, dpi = ret[rank]
+        assert same_shape
+        assert ds < 1e-10, ds
+        assert dpi < 1e-7, dpi
+    assert ret[0][1:] == ret[1][1:]          # both ranks hold identical results
