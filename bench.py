@@ -193,7 +193,13 @@ def run_b200(args):
 
     if world > 1:
         from acetn_b200.distributed import ShardedCtmrg
-        gsz = args.group_size or (2 if world >= 8 else 1)
+        # ranks per projector: 1 while there are at least as many site tasks per phase (2*min(nx,ny)) as ranks; beyond
+        # that, pairs of ranks compute one projector cooperatively (row-sharded, acetn_b200/sharded_projector.py)
+        gsz = args.group_size
+        if not gsz:
+            gsz = 1
+            while world // gsz > 2 * min(nx, ny) and world % (2 * gsz) == 0:
+                gsz *= 2
         sharded = ShardedCtmrg(ip, cfg, rank, world, group_size=gsz)
         sweep = sharded.sweep
     else:
