@@ -215,3 +215,48 @@ def test_absorption(D, chi, d, seed):
         ref_e = orc.absorb_edge(st.E[(3 + k) % 4], st.bond_permute(k), pj2, pj1)
         assert e.shape == ref_e.shape
         assert rel(e.cpu(), ref_e) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- K1 fuzz
+def _rand_operand(rng, rows, cols, nb):
+    """A (rows x cols) logical matrix per batch stored inside a random larger tensor, with a random two-level split of
+    each index group.  Returns (tensor, ptr_tensor, idx9, dense) where idx9 = {div,s_hi,s_lo} for (row, col, batch)."""
+    def split(n):
+        divs = [d for d in range(2, n) if n % d == 0]
+        if divs and rng.random() < 0.6:
+            d = divs[int(rng.integers(len(divs)))]
+            return n // d, d           # (hi extent, lo extent)
+        return 1, n
+    rh, rl = split(rows)
+    ch, cl = split(cols)
+    # storage order: a random permutation of the legs (b, rh, rl, ch, cl), contiguous
+    legs = {"b": nb, "rh": rh, "rl": rl, "ch": ch, "cl": cl}
+    order = list(legs)
+    rng.shuffle(order)
+    shape = [legs[k] for k in order]
+    t = torch.from_numpy(rng.standard_normal(shape)).to(DEV)
+    strides = dict(zip(order, t.stride()))
+    dense = t.permute([order.index(k) for k in ("b", "rh", "rl", "ch", "cl")]).reshape(nb, rows, cols)
+    idx = [rl if rh > 1 else 0, strides["rh"] if rh > 1 else 0, strides["rl"],
+           cl if ch > 1 else 0, strides["ch"] if ch > 1 else 0, strides["cl"],
+           0, 0, strides["b"] if nb > 1 else 0]
+    return t, idx, dense
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_gemm_fuzz_two_level_descriptors(seed):
+    """Random shapes, leg orders (all four smem orientations + scalar/vector loaders), two-level splits, batches,
+    alpha/beta, tiles and split-K against torch.einsum."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    M, N, K = (int(rng.integers(1, 200)) for _ in range(3))
+    nb = int(rng.integers(1, 4))
+    A_t, a_idx, A_d = _rand_operand(rng, M, K, nb)
+    B_t, b_idx, B_d = _rand_operand(rng, K, N, nb)
+    C_t, c_idx, C_d = _rand_operand(rng, M, N, nb)
+    alpha, beta = float(rng.standard_normal()), float(rng.choice([0.0, 1.0, -0.5]))
+    ref = alpha * torch.einsum("bmk,bkn->bmn", A_d, B_d) + beta * C_d
+    tile = int(rng.choice([0, 1, 2, 3, 5, 6, 7]))
+    splitk = int(rng.choice([0, 0, 2, 3])) if K >= 128 else 0
+    ops.gemm_ex(M, N, K, nb, A_t, B_t, C_t, a_idx + b_idx + c_idx, alpha=alpha, beta=beta, force_tile=tile, force_splitk=splitk)
+    assert rel(C_d, ref) < 1e-12
