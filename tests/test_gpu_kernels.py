@@ -236,7 +236,7 @@ def _rand_operand(rng, rows, cols, nb):
     shape = [legs[k] for k in order]
     t = torch.from_numpy(rng.standard_normal(shape)).to(DEV)
     strides = dict(zip(order, t.stride()))
-    dense = t.permute([order.index(k) for k in ("b", "rh", "rl", "ch", "cl")]).reshape(nb, rows, cols)
+    dense = lambda: t.permute([order.index(k) for k in ("b", "rh", "rl", "ch", "cl")]).reshape(nb, rows, cols)   # noqa: E731
     idx = [rl if rh > 1 else 0, strides["rh"] if rh > 1 else 0, strides["rl"],
            cl if ch > 1 else 0, strides["ch"] if ch > 1 else 0, strides["cl"],
            0, 0, strides["b"] if nb > 1 else 0]
@@ -255,8 +255,8 @@ def test_gemm_fuzz_two_level_descriptors(seed):
     B_t, b_idx, B_d = _rand_operand(rng, K, N, nb)
     C_t, c_idx, C_d = _rand_operand(rng, M, N, nb)
     alpha, beta = float(rng.standard_normal()), float(rng.choice([0.0, 1.0, -0.5]))
-    ref = alpha * torch.einsum("bmk,bkn->bmn", A_d, B_d) + beta * C_d
+    ref = alpha * torch.einsum("bmk,bkn->bmn", A_d(), B_d()) + beta * C_d()
     tile = int(rng.choice([0, 1, 2, 3, 5, 6, 7]))
     splitk = int(rng.choice([0, 0, 2, 3])) if K >= 128 else 0
     ops.gemm_ex(M, N, K, nb, A_t, B_t, C_t, a_idx + b_idx + c_idx, alpha=alpha, beta=beta, force_tile=tile, force_splitk=splitk)
-    assert rel(C_d, ref) < 1e-12
+    assert rel(C_d(), ref) < 1e-12
