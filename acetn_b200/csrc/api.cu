@@ -453,8 +453,8 @@ size_t acetn_b200_absorb_edge_workspace_bytes(int64_t xa, int64_t xb, int64_t xx
     return b + maxz(g, dl_workspace_bytes(xa, xx, D, d)) + 4096;
 }
 int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_strides, const double* proj2, const double* proj1,
-                           int64_t xa, int64_t xb, int64_t xx, int64_t xy, int64_t D, int64_t d, double* out, void* wsp,
-                           size_t ws_bytes, void* stream) {
+                           int64_t xa, int64_t xb, int64_t xx, int64_t xy, int64_t D, int64_t d, int normalize, double* out,
+                           void* wsp, size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     EdgeDims e{xa, xb, xx, xy, D, d};
     const int64_t D2 = D * D, D4 = D2 * D2;
@@ -481,6 +481,7 @@ int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_s
     for (int i = 0; i < 5; i++) a.a_s[i] = a_strides[i];
     AB_TRY(double_layer(a, nullptr, g, gb, s));
     AB_TRY(gemm_launch(e_g4(e, proj2, T3, out), g, gb, s));        // out[y,(x,r,R)]
+    if (!normalize) return OK;                                     // partial sum of a row-sharded absorption
     return frob_normalize_launch(out, (size_t)(xy * xx * D2), fs, s);
 }
 

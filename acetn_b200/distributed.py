@@ -82,6 +82,26 @@ class B200Compute:
         del pend
         return [(a.contiguous(), b.contiguous()) for a, b in out]
 
+    def absorb_coop(self, ipeps, task, p1i, p2i, p1j, p2j, group, g, G):
+        """Cooperative absorption by the G ranks of a group: the two corners are tiny and replicated; the edge
+        contraction is linear in the leg `a` shared by ei and proj2, so rank g contracts its a-block and the
+        un-normalised partial results are all-reduced, then normalised identically on every rank."""
+        k = task["k"]
+        src = ipeps[task["s1"]]
+        m = self.mover
+        c1 = m.renormalize_cj1(src['C'][(3 + k) % 4], src['E'][(2 + k) % 4], p1i)
+        c2 = m.renormalize_cj2(src['C'][k], src['E'][k], p2j)
+        ei = src['E'][(3 + k) % 4]
+        a0, a1 = _a_block(ei.shape[0], G, g)
+        from . import ops
+        if a1 > a0:
+            e = ops.absorb_edge(ei[a0:a1].contiguous(), src.bond_permute(k), p2i[a0:a1].contiguous(), p1j, normalize=False)
+        else:
+            e = torch.zeros(p2i.shape[3], p1j.shape[3], ei.shape[2], ei.shape[3], dtype=ei.dtype, device=ei.device)
+        dist.all_reduce(e, op=dist.ReduceOp.SUM, group=group)
+        ops.frob_normalize(e)
+        return c1, c2, e
+
     def absorb(self, ipeps, task, p1i, p2i, p1j, p2j):
         """The three absorptions of one task (directional_mover.py:293-303) -> (C[(3+k)%4], C[k], E[(3+k)%4]) of site s2."""
         k = task["k"]
@@ -91,6 +111,12 @@ class B200Compute:
         c2 = m.renormalize_cj2(src['C'][k], src['E'][k], p2j)
         e = m.renormalize_ej(src['E'][(3 + k) % 4], src.bond_permute(k), p2i, p1j)
         return c1, c2, e
+
+
+def _a_block(n, G, g):
+    base, rem = divmod(n, G)
+    start = g * base + min(g, rem)
+    return start, start + base + (1 if g < rem else 0)
 
 
 def phase_moves(ipeps):
@@ -180,12 +206,21 @@ class ShardedCtmrg:
                 p2 = torch.empty(chi2, D, D, keep[n], dtype=dtype, device=device)
             P1[(t["k"], t["key"])] = self._bcast(p1, self.owner(n))
             P2[(t["k"], t["key"])] = self._bcast(p2, self.owner(n))
-        # owners absorb
+        # owners absorb (G > 1: every rank of the owning group takes part in each of the group's absorptions)
         results = {}
-        for n in mine:
-            t = tasks[n]
-            k = t["k"]
-            results[n] = cp.absorb(ip, t, P1[(k, t["i"])], P2[(k, t["i"])], P1[(k, t["j"])], P2[(k, t["j"])])
+        if self.G > 1 and hasattr(cp, "absorb_coop"):
+            for n in coop:
+                t = tasks[n]
+                k = t["k"]
+                res = cp.absorb_coop(ip, t, P1[(k, t["i"])], P2[(k, t["i"])], P1[(k, t["j"])], P2[(k, t["j"])], self.pair_group,
+                                     self.g, self.G)
+                if self.owner(n) == rank:
+                    results[n] = res
+        else:
+            for n in mine:
+                t = tasks[n]
+                k = t["k"]
+                results[n] = cp.absorb(ip, t, P1[(k, t["i"])], P2[(k, t["i"])], P1[(k, t["j"])], P2[(k, t["j"])])
         # publish the new boundary tensors (all reads of this phase are done: the writes touch tensors no task reads)
         for n, t in enumerate(tasks):
             k = t["k"]

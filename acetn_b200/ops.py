@@ -250,8 +250,8 @@ def absorb_corner2(ci, ei, proj):
     return out
 
 
-def absorb_edge(ei, A_view, proj2, proj1):
-    """directional_mover.py:345-366 : out[y,x,r,R]."""
+def absorb_edge(ei, A_view, proj2, proj1, normalize=True):
+    """directional_mover.py:345-366 : out[y,x,r,R].  normalize=False: un-normalised (partial) result."""
     dev = _require_cuda(ei, A_view, proj2, proj1)
     ei, proj1, proj2 = ei.contiguous(), proj1.contiguous(), proj2.contiguous()
     xa, xb, D = ei.shape[0], ei.shape[1], ei.shape[2]
@@ -264,7 +264,7 @@ def absorb_edge(ei, A_view, proj2, proj1):
     ws = _ws(dev, lib.acetn_b200_absorb_edge_workspace_bytes(xa, xb, xx, xy, D, d))
     with torch.cuda.device(dev):
         st = lib.acetn_b200_absorb_edge(_p(ei), _p(A_view), _lib.i64_array(A_view.stride()), _p(proj2), _p(proj1), xa, xb, xx, xy, D, d,
-                                        _p(out), _p(ws), ws.numel(), _stream(dev))
+                                        1 if normalize else 0, _p(out), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_edge")
     return out
 
@@ -341,6 +341,17 @@ def absmax(x, out):
         st = _lib.load().acetn_b200_absmax(_p(x), x.numel(), _p(out), _stream(dev))
     _lib.check(st, "absmax")
     return out
+
+
+def frob_normalize(x):
+    """x /= ||x||_F in place (deterministic two-stage reduction)."""
+    dev = _require_cuda(x)
+    assert x.is_contiguous()
+    ws = _ws(dev, 8192 * 8)
+    with torch.cuda.device(dev):
+        st = _lib.load().acetn_b200_frob_normalize(_p(x), x.numel(), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "frob_normalize")
+    return x
 
 
 def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):

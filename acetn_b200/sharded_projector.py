@@ -80,6 +80,12 @@ class ShardedHalfSystemProjector:
 
     def _forward(self, Qg, rows, X, nrows_total):
         """full (nrows_total x q) = Q X from this rank's row block Qg = Q[rows]."""
+        if self.G > 1 and nrows_total % self.G == 0 and rows[1] - rows[0] == nrows_total // self.G:
+            # equal row blocks: plain all-gather of the blocks (half the traffic of the zero-padded all-reduce)
+            out = torch.empty(nrows_total, X.shape[1], dtype=X.dtype, device=X.device)
+            blk = self.la.matmul(Qg, X, out=out[rows[0]:rows[1]])
+            dist.all_gather_into_tensor(out, blk, group=self.group)
+            return out
         out = torch.zeros(nrows_total, X.shape[1], dtype=X.dtype, device=X.device)
         if rows[1] > rows[0]:
             self.la.matmul(Qg, X, out=out[rows[0]:rows[1]])

@@ -115,7 +115,9 @@ int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, con
  *   corner1: out[a,x] = sum ei[a,b,l,L] ci[b,c] proj[c,l,L,x] / ||.||     ci (chi_b,chi_c) ei (chi_a,chi_b,D,D) proj (chi_c,D,D,chi_x)
  *   corner2: out[x,c] = sum proj[a,r,R,x] ci[a,b] ei[b,c,r,R] / ||.||     ci (chi_a,chi_b) ei (chi_b,chi_c,D,D) proj (chi_a,D,D,chi_x)
  *   edge   : out[y,x,r,R] = sum ei[a,b,l,L] proj1[b,u,U,x] conj(A)[L,U,R,D,P] A[l,u,r,d,P] proj2[a,d,D,y] / ||.||
- *            ei (chi_a,chi_b,D,D), proj1 (chi_b,D,D,chi_x), proj2 (chi_a,D,D,chi_y), A = bond_permute(k) view. */
+ *            ei (chi_a,chi_b,D,D), proj1 (chi_b,D,D,chi_x), proj2 (chi_a,D,D,chi_y), A = bond_permute(k) view.
+ *            normalize = 0 returns the un-normalised sum: the contraction is linear in the `a` leg shared by ei and
+ *            proj2, so ranks holding a-blocks of both can all-reduce their partial results and normalise afterwards. */
 size_t acetn_b200_absorb_corner_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_x, int64_t D);
 int acetn_b200_absorb_corner1(const double* ci, const double* ei, const double* proj, int64_t chi_a, int64_t chi_b,
                               int64_t chi_c, int64_t chi_x, int64_t D, double* out, void* ws, size_t ws_bytes,
@@ -127,7 +129,7 @@ size_t acetn_b200_absorb_edge_workspace_bytes(int64_t chi_a, int64_t chi_b, int6
                                               int64_t d);
 int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_strides, const double* proj2,
                            const double* proj1, int64_t chi_a, int64_t chi_b, int64_t chi_x, int64_t chi_y, int64_t D,
-                           int64_t d, double* out, void* ws, size_t ws_bytes, void* stream);
+                           int64_t d, int normalize, double* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- double-layer site absorption on its own (K2; the `cuUelL,LURDP->cuelRDP` + `lurdp,cuelRDp->crRedD` pair of
  *      projectors.py:54-55 and the matching pair of directional_mover.py:363-364), exposed for tests/benchmarks.

@@ -41,6 +41,21 @@ class OracleCompute:
                 out.append(orc.half_system_projectors(cell, t["plaq"], t["k"], self.cfg, omega_fn=lambda n, q, dt=None, dv=None, om=om: om))
         return [(a.contiguous(), b.contiguous()) for a, b in out]
 
+    def absorb_coop(self, cell, task, p1i, p2i, p1j, p2j, group, g, G):
+        """Row-sharded edge absorption (un-normalised partials over the shared leg a, summed, then normalised)."""
+        from acetn_b200.distributed import _a_block
+        k, a = task["k"], cell[task["s1"]]
+        c1 = orc.absorb_corner1(a.C[(3 + k) % 4], a.E[(2 + k) % 4], p1i)
+        c2 = orc.absorb_corner2(a.C[k], a.E[k], p2j)
+        ei, ai = a.E[(3 + k) % 4], a.bond_permute(k)
+        a0, a1 = _a_block(ei.shape[0], G, g)
+        t = torch.einsum("ablL,buUx->alLuUx", ei[a0:a1], p1j)
+        t = torch.einsum("LURDP,alLuUx->RDPalux", ai.conj(), t)
+        t = torch.einsum("lurdp,RDpalux->rdRDax", ai, t)
+        e = torch.einsum("rdRDax,adDy->yxrR", t, p2i[a0:a1]).contiguous()
+        dist.all_reduce(e, op=dist.ReduceOp.SUM, group=group)
+        return c1, c2, e / e.norm()
+
     def absorb(self, cell, task, p1i, p2i, p1j, p2j):
         k, a = task["k"], cell[task["s1"]]
         return (orc.absorb_corner1(a.C[(3 + k) % 4], a.E[(2 + k) % 4], p1i), orc.absorb_corner2(a.C[k], a.E[k], p2j),
