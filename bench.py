@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-size", type=int, default=0, help="ranks cooperating on one projector (0 = auto)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' times the reference torch path (cuBLAS/cuSOLVER) on the GPU instead of the host cores")
     return ap.parse_args()
 
 
@@ -84,11 +86,6 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
-
-
-def synthetic_cell(args, nx, ny):
-    from oracle import ctmrg_oracle as orc   # shared synthetic-input generator; inputs only
-    return orc.random_cell(nx, ny, args.D, args.chi, args.d, seed=args.seed)
 
 
 def cpu_site_move_seconds(args, reps=1):
@@ -142,8 +139,9 @@ def run_reference(args):
     if rank != 0:
         return
     times = []
+    on_gpu = args.ref_device == "cuda"
     for i in range(args.warmup + args.steps):
-        t = cpu_site_move_seconds(args)
+        t = gpu_torch_site_move_seconds(args, torch.device("cuda", 0)) if on_gpu else cpu_site_move_seconds(args)
         if i >= args.warmup:
             times.append(t)
     t_move = sum(times) / len(times)
@@ -155,7 +153,8 @@ def run_reference(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"CTMRG sweep, D={args.D} chi={args.chi} d={args.d}, {'2x2' if args.gpus <= 1 else '4x4'} cell "
                                    f"({16 if args.gpus <= 1 else 64} site-moves/sweep), half-system rsvd niter=2 p=2",
-                       "value_unit": "sweeps of 16 site-moves per second", "device": "cpu (reference torch path, oracle port)"},
+                       "value_unit": "sweeps of 16 site-moves per second",
+                       "device": "cuda (reference torch path = cuBLAS/cuSOLVER via torch, oracle port)" if on_gpu else "cpu (reference torch path, oracle port)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -166,9 +165,9 @@ def run_b200(args):
     import torch.distributed as dist
 
     from acetn_b200 import _lib, ops
-    from acetn_b200.ipeps import CTMRGConfig, Ipeps, SiteTensor
+    from acetn_b200.ipeps import CTMRGConfig, SiteTensor
     from acetn_b200.renormalization import DirectionalMover, ctmrg
-    from oracle import ctmrg_oracle as orc
+    from acetn_b200.synthetic import flops_sweep, random_ipeps
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,9 +184,8 @@ def run_b200(args):
     ny = args.ny or (2 if n == 1 else 4)
     D, chi, d = args.D, args.chi, args.d
 
-    cell = synthetic_cell(args, nx, ny)
     cfg = CTMRGConfig(steps=1)
-    ip = Ipeps.from_plain(cell, cfg, device=dev)
+    ip = random_ipeps(nx, ny, D, chi, d, seed=args.seed, ctmrg=cfg, device=dev)
     mover = DirectionalMover(cfg)
     torch.manual_seed(args.seed + 1)      # Omega stream (device generator), identical on every rank
 
@@ -313,7 +311,7 @@ def run_b200(args):
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "kernel": "dgemm_dmma_kernel (K1), thin GEMM %dx%dx%d" % (m, q, m),
                     "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 entry)",
-                    "whole_sweep_tflops": orc.flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n,
+                    "whole_sweep_tflops": flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n,
                     # 13 thin DGEMMs per site-move (12 rSVD + proj2), per rank; share = their summed duration / step time
                     "launches_per_step": 13 * site_moves // n,
                     "share_of_step": (13 * site_moves / n) * t_gemm / (ms * 1e-3 / args.steps)}
@@ -335,14 +333,7 @@ def run_b200(args):
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if n == 1 and not args.no_cpu_baseline:
-            try:
-                t_gpu = gpu_torch_site_move_seconds(args, dev)
-                line["gpu_torch_baseline"] = {"value": 1.0 / (16.0 * t_gpu), "unit": UNIT, "kind": "port",
-                                              "sample": f"one site-move of the reference torch path (cuBLAS/cuSOLVER via torch) on this GPU, "
-                                                        f"{t_gpu * 1e3:.1f} ms, scaled x16 to a 2x2 sweep"}
-            except Exception as ex:   # noqa: BLE001  (baseline only; never affects the measured arm)
-                line["gpu_torch_baseline"] = {"unavailable": str(ex)[:200]}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

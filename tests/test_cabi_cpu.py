@@ -81,3 +81,17 @@ def test_host_mirror_error_behaviour():
     with pytest.raises(ValueError):
         ip[(3, 3)]
     assert len(ip.bond_list) == 2 and ip.bond_list[0][2] == 2 and ip.bond_list[1][2] == 1
+
+
+def test_synthetic_inputs_match_oracle_generator():
+    """bench.py's product arm builds its inputs with acetn_b200.synthetic (no oracle import on the product path); the
+    generator must produce exactly the tensors the oracle-side tests use and the same flop model."""
+    from acetn_b200.synthetic import flops_sweep, random_ipeps
+    from oracle import ctmrg_oracle as orc
+    ip = random_ipeps(2, 3, 3, 5, 2, seed=7, device="cpu")
+    cell = orc.random_cell(2, 3, 3, 5, 2, seed=7)
+    for s in cell.site_list:
+        assert torch.equal(ip[s]['A'], cell[s].A)
+        for k in range(4):
+            assert torch.equal(ip[s]['C'][k], cell[s].C[k]) and torch.equal(ip[s]['E'][k], cell[s].E[k])
+    assert flops_sweep(2, 2, 8, 256) == orc.flops_sweep(2, 2, 8, 256)
