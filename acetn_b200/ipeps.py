@@ -1,7 +1,7 @@
 """Minimal stand-alone substrate with the reference's accessors (acetn/ipeps/{site_tensor,tensor_network,ipeps,
 ipeps_config}.py) so the B200 path can run where the reference package is not installed (the GPU box).  When the
 reference *is* installed, use acetn_b200.integration.install() and the reference's own Ipeps instead."""
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict
 
 import torch

@@ -288,7 +288,6 @@ class DirectionalMover:
         tasks = []
         for k, line in moves:
             tasks += self.move_tasks(ipeps, k, line)
-        plaq = [((t["k"], t["key"]), t["plaq"]) for t in tasks]
         p1, p2 = self._projectors_of_tasks(ipeps, tasks)
         for t in tasks:
             k = t["k"]
