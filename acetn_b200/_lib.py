@@ -46,6 +46,17 @@ SIGNATURES = {
     "acetn_b200_double_layer_workspace_bytes": (c_sz, [c_i64] * 4),
     "acetn_b200_double_layer": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, P_i64, c_int, c_vp, P_i64, c_i64, c_i64, c_vp, c_i64,
                                         c_i64, P_i64, c_vp, c_sz, c_vp]),
+    "acetn_b200_i8_supported": (c_int, [c_i64, c_i64, c_i64]),
+    "acetn_b200_i8_encoded_bytes": (c_sz, [c_i64, c_i64]),
+    "acetn_b200_i8_encode": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "acetn_b200_i8_matmul_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "acetn_b200_i8_matmul": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "acetn_b200_rsvd_enc_workspace_bytes": (c_sz, [c_int, P_i64, P_i64, c_i64, ctypes.POINTER(ctypes.c_int32)]),
+    "acetn_b200_rsvd_enc": (c_int, [c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), P_i64, P_i64, c_vp, c_i64, c_int, c_int, c_i64, c_dbl,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_projectors_enc_workspace_bytes": (c_sz, [c_i64] * 5 + [c_int]),
+    "acetn_b200_projectors_from_usv_enc": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                                   c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_fp64_peak_probe": (c_dbl, [c_vp, c_int, c_vp]),
     "acetn_b200_als_workspace_bytes": (c_sz, [c_i64] * 3),
     "acetn_b200_als_solve": (c_int, [c_vp] * 5 + [c_i64] * 4 + [c_dbl, c_dbl, c_vp, c_vp, c_sz, c_vp]),

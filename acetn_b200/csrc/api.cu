@@ -4,6 +4,7 @@
 #include "../../include/acetn_b200.h"
 
 #include "gemm.cuh"
+#include "i8crt.cuh"
 #include "kernels.cuh"
 
 using namespace ab200;
@@ -204,12 +205,27 @@ int acetn_b200_jacobi_svd(const double* R, int64_t q, double* S, double* Wt, dou
     return jacobi_svd_launch(R, (int)q, S, Wt, Jt, (int)chi, cutoff, (int*)info, ws, ws_bytes, S_(stream));
 }
 
+// ---- K7: INT8 tensor-core exact products ------------------------------------------------------------------------------
+int acetn_b200_i8_supported(int64_t rows, int64_t cols, int64_t q) { return i8_supported(rows, cols, q) ? 1 : 0; }
+size_t acetn_b200_i8_encoded_bytes(int64_t rows, int64_t cols) { return i8_encoded_bytes(rows, cols); }
+int acetn_b200_i8_encode(const double* Q, int64_t rows, int64_t cols, int64_t ldq, void* storage, size_t storage_bytes, void* stream) {
+    I8Matrix e;
+    return i8_encode_launch(Q, rows, cols, ldq, storage, storage_bytes, &e, S_(stream));
+}
+size_t acetn_b200_i8_matmul_workspace_bytes(int64_t rows, int64_t cols, int64_t q) { return i8_matmul_workspace_bytes(rows, cols, q); }
+int acetn_b200_i8_matmul(const void* storage, int64_t rows, int64_t cols, int adjoint, const double* Y, int64_t q, int64_t ldy,
+                         double* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream) {
+    AB_REQUIRE(i8_supported(rows, cols, q), "i8_matmul: unsupported shape (%lld x %lld, q=%lld)", (long long)rows, (long long)cols, (long long)q);
+    return i8_matmul_launch(i8_view(storage, rows, cols), adjoint != 0, Y, q, ldy, out, ldo, ws, ws_bytes, S_(stream));
+}
+
 // ---- randomized SVD -----------------------------------------------------------------------------------------------------
 namespace {
 struct Chain {
     int n;
     const double* mat[4];
     int64_t rows[4], cols[4];
+    const void* enc[4];      // K7 residue encoding of mat[i] (or NULL: FP64 DMMA path, K1)
 };
 // out (rows x q) = M (rows x cols) * in (cols x q)      /   out (cols x q) = M^T * in (rows x q)
 GemmDesc thin_desc(const double* M, int64_t rows, int64_t cols, bool adjoint, const double* in, double* out, int64_t q) {
@@ -220,10 +236,17 @@ GemmDesc thin_desc(const double* M, int64_t rows, int64_t cols, bool adjoint, co
 size_t chain_gemm_ws(const Chain& c, int64_t q) {
     size_t g = 0;
     for (int i = 0; i < c.n; i++) {
+        if (c.enc[i] != nullptr) { g = maxz(g, i8_matmul_workspace_bytes(c.rows[i], c.cols[i], q)); continue; }
         g = maxz(g, gemm_workspace_bytes(thin_desc(nullptr, c.rows[i], c.cols[i], false, nullptr, nullptr, q)));
         g = maxz(g, gemm_workspace_bytes(thin_desc(nullptr, c.rows[i], c.cols[i], true, nullptr, nullptr, q)));
     }
     return g;
+}
+// one "big x thin" product: K7 (INT8 tensor cores, exact) when the factor carries an encoding, else K1 (FP64 DMMA)
+int thin_apply(const Chain& c, int i, bool adjoint, const double* in, double* out, int64_t q, void* gws, size_t gws_bytes, cudaStream_t s) {
+    if (c.enc[i] != nullptr)
+        return i8_matmul_launch(i8_view(c.enc[i], c.rows[i], c.cols[i]), adjoint, in, q, q, out, q, gws, gws_bytes, s);
+    return gemm_launch(thin_desc(c.mat[i], c.rows[i], c.cols[i], adjoint, in, out, q), gws, gws_bytes, s);
 }
 // forward: out = M0 M1 ... Mn-1 in ;  adjoint: out = Mn-1^T ... M0^T in
 int chain_apply(const Chain& c, bool adjoint, const double* in, double* out, double* t0, double* t1, int64_t q, void* gws,
@@ -232,7 +255,7 @@ int chain_apply(const Chain& c, bool adjoint, const double* in, double* out, dou
     for (int step = 0; step < c.n; step++) {
         int i = adjoint ? step : (c.n - 1 - step);
         double* dst = (step == c.n - 1) ? out : ((step & 1) ? t1 : t0);
-        AB_TRY(gemm_launch(thin_desc(c.mat[i], c.rows[i], c.cols[i], adjoint, src, dst, q), gws, gws_bytes, s));
+        AB_TRY(thin_apply(c, i, adjoint, src, dst, q, gws, gws_bytes, s));
         src = dst;
     }
     return OK;
@@ -252,8 +275,15 @@ GemmDesc lift_desc(const double* Qm, int64_t rows, int64_t q, const double* Wt, 
 }  // namespace
 
 size_t acetn_b200_rsvd_workspace_bytes(int nmat, const int64_t* rows, const int64_t* cols, int64_t q) {
+    return acetn_b200_rsvd_enc_workspace_bytes(nmat, rows, cols, q, nullptr);
+}
+size_t acetn_b200_rsvd_enc_workspace_bytes(int nmat, const int64_t* rows, const int64_t* cols, int64_t q, const int32_t* use_enc) {
     Chain c; c.n = nmat;
-    for (int i = 0; i < nmat; i++) { c.mat[i] = nullptr; c.rows[i] = rows[i]; c.cols[i] = cols[i]; }
+    static const char marker = 0;
+    for (int i = 0; i < nmat; i++) {
+        c.mat[i] = nullptr; c.rows[i] = rows[i]; c.cols[i] = cols[i];
+        c.enc[i] = (use_enc != nullptr && use_enc[i]) ? (const void*)&marker : nullptr;
+    }
     const int64_t m = rows[0], n = cols[nmat - 1], mx = chain_maxdim(c);
     size_t b = ws_round((size_t)(m * q) * 8) + 2 * ws_round((size_t)(mx * q) * 8) + 2 * ws_round((size_t)(n * q) * 8) +
                3 * ws_round((size_t)(q * q) * 8);
@@ -270,11 +300,21 @@ size_t acetn_b200_rsvd_workspace_bytes(int nmat, const int64_t* rows, const int6
 int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, const int64_t* cols, const double* Omega, int64_t q,
                     int niter, int reorth_adjoint, int64_t chi, double cutoff, double* U, double* S, double* V, int32_t* info,
                     double* AtQ, double* Wt_out, void* wsp, size_t ws_bytes, void* stream) {
+    return acetn_b200_rsvd_enc(nmat, mats, nullptr, rows, cols, Omega, q, niter, reorth_adjoint, chi, cutoff, U, S, V, info, AtQ, Wt_out,
+                               wsp, ws_bytes, stream);
+}
+int acetn_b200_rsvd_enc(int nmat, const double* const* mats, const void* const* encs, const int64_t* rows, const int64_t* cols,
+                        const double* Omega, int64_t q, int niter, int reorth_adjoint, int64_t chi, double cutoff, double* U, double* S,
+                        double* V, int32_t* info, double* AtQ, double* Wt_out, void* wsp, size_t ws_bytes, void* stream) {
     cudaStream_t s = S_(stream);
     AB_REQUIRE(nmat >= 1 && nmat <= 4, "rsvd: nmat must be 1..4");
     Chain c; c.n = nmat;
     for (int i = 0; i < nmat; i++) {
-        c.mat[i] = mats[i]; c.rows[i] = rows[i]; c.cols[i] = cols[i];
+        c.mat[i] = mats != nullptr ? mats[i] : nullptr; c.rows[i] = rows[i]; c.cols[i] = cols[i];
+        c.enc[i] = encs != nullptr ? encs[i] : nullptr;
+        AB_REQUIRE(c.mat[i] != nullptr || c.enc[i] != nullptr, "rsvd: factor %d has neither FP64 data nor an encoding", i);
+        AB_REQUIRE(c.enc[i] == nullptr || i8_supported(rows[i], cols[i], q), "rsvd: factor %d (%lld x %lld, q=%lld) is outside the INT8 engine's range",
+                   i, (long long)rows[i], (long long)cols[i], (long long)q);
         if (i > 0) AB_REQUIRE(cols[i - 1] == rows[i], "rsvd: inner dimensions of factors %d and %d differ", i - 1, i);
     }
     const int64_t m = rows[0], n = cols[nmat - 1], mx = chain_maxdim(c);
@@ -302,9 +342,9 @@ int acetn_b200_rsvd(int nmat, const double* const* mats, const int64_t* rows, co
     AB_TRY(orthonormalize_launch(Y, m, (int)q, q, g, gb, s));                      // Q
     if (AtQ != nullptr && c.n >= 2) {
         // keep M0^T Q (the first product of the adjoint chain): proj1 = M0^T U = (M0^T Q) U_B needs no further pass over M0
-        AB_TRY(gemm_launch(thin_desc(c.mat[0], c.rows[0], c.cols[0], true, Y, AtQ, q), g, gb, s));
+        AB_TRY(thin_apply(c, 0, true, Y, AtQ, q, g, gb, s));
         Chain rest; rest.n = c.n - 1;
-        for (int i = 1; i < c.n; i++) { rest.mat[i - 1] = c.mat[i]; rest.rows[i - 1] = c.rows[i]; rest.cols[i - 1] = c.cols[i]; }
+        for (int i = 1; i < c.n; i++) { rest.mat[i - 1] = c.mat[i]; rest.rows[i - 1] = c.rows[i]; rest.cols[i - 1] = c.cols[i]; rest.enc[i - 1] = c.enc[i]; }
         AB_TRY(chain_apply(rest, true, AtQ, Z, t0, t1, q, g, gb, s));
     } else {
         AB_TRY(chain_apply(c, true, Y, Z, t0, t1, q, g, gb, s));                  // Z = Bt^T  (n x q),  Bt = Q^H M
@@ -330,18 +370,34 @@ GemmDesc p2_desc(const double* Q4, int64_t m4, int64_t n4, const double* Vs, int
 }
 }  // namespace
 size_t acetn_b200_projectors_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep) {
+    return acetn_b200_projectors_enc_workspace_bytes(m1, n1, m4, n4, keep, 0);
+}
+size_t acetn_b200_projectors_enc_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep, int use_enc) {
     const int64_t qmax = m1 < n4 ? m1 : n4;          // q <= min(m, n)
     size_t b = ws_round((size_t)(m1 * keep) * 8) + ws_round((size_t)(n4 * keep) * 8) + ws_round((size_t)keep * 8) +
                2 * ws_round((size_t)(qmax * keep) * 8);
     size_t g = maxz(gemm_workspace_bytes(p1_desc(nullptr, m1, n1, nullptr, keep, nullptr)),
                     gemm_workspace_bytes(p2_desc(nullptr, m4, n4, nullptr, keep, nullptr)));
+    if (use_enc) g = maxz(g, maxz(i8_matmul_workspace_bytes(m1, n1, keep), i8_matmul_workspace_bytes(m4, n4, keep)));
     return b + g + 4096;
 }
 int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, const double* Q4, int64_t m4, int64_t n4,
                                    const double* U, int64_t ldu, const double* V, int64_t ldv, const double* S, int64_t keep,
                                    const double* qmax1, const double* qmax4, const double* AtQ, const double* Wt, int64_t q,
                                    double* proj1, double* proj2, void* wsp, size_t ws_bytes, void* stream) {
+    return acetn_b200_projectors_from_usv_enc(Q1, nullptr, m1, n1, Q4, nullptr, m4, n4, U, ldu, V, ldv, S, keep, qmax1, qmax4, AtQ, Wt, q,
+                                              proj1, proj2, wsp, ws_bytes, stream);
+}
+int acetn_b200_projectors_from_usv_enc(const double* Q1, const void* enc1, int64_t m1, int64_t n1, const double* Q4, const void* enc4,
+                                       int64_t m4, int64_t n4, const double* U, int64_t ldu, const double* V, int64_t ldv,
+                                       const double* S, int64_t keep, const double* qmax1, const double* qmax4, const double* AtQ,
+                                       const double* Wt, int64_t q, double* proj1, double* proj2, void* wsp, size_t ws_bytes,
+                                       void* stream) {
     cudaStream_t s = S_(stream);
+    AB_REQUIRE(enc1 == nullptr || i8_supported(m1, n1, keep), "projectors: Q1 is outside the INT8 engine's range");
+    AB_REQUIRE(enc4 == nullptr || i8_supported(m4, n4, keep), "projectors: Q4 is outside the INT8 engine's range");
+    AB_REQUIRE(AtQ != nullptr || Q1 != nullptr || enc1 != nullptr, "projectors: Q1 needs FP64 data or an encoding");
+    AB_REQUIRE(Q4 != nullptr || enc4 != nullptr, "projectors: Q4 needs FP64 data or an encoding");
     AB_REQUIRE(keep >= 1, "projectors: keep must be >= 1");
     AB_REQUIRE((AtQ == nullptr) == (Wt == nullptr), "projectors: AtQ and Wt must be given together");
     Workspace ws(wsp, ws_bytes);
@@ -367,9 +423,11 @@ int acetn_b200_projectors_from_usv(const double* Q1, int64_t m1, int64_t n1, con
                                      idx1(keep), idx1(1)), g, gb, s));
     } else {
         AB_TRY(scale_cols_launch(Us, keep, U, ldu, w, qmax1, m1, (int)keep, s));
-        AB_TRY(gemm_launch(p1_desc(Q1, m1, n1, Us, keep, proj1), g, gb, s));
+        if (enc1 != nullptr) AB_TRY(i8_matmul_launch(i8_view(enc1, m1, n1), true, Us, keep, keep, proj1, keep, g, gb, s));
+        else AB_TRY(gemm_launch(p1_desc(Q1, m1, n1, Us, keep, proj1), g, gb, s));
     }
-    AB_TRY(gemm_launch(p2_desc(Q4, m4, n4, Vs, keep, proj2), g, gb, s));
+    if (enc4 != nullptr) AB_TRY(i8_matmul_launch(i8_view(enc4, m4, n4), false, Vs, keep, keep, proj2, keep, g, gb, s));
+    else AB_TRY(gemm_launch(p2_desc(Q4, m4, n4, Vs, keep, proj2), g, gb, s));
     return OK;
 }
 

@@ -370,3 +370,50 @@ def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
                                       _p(info), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "als_solve")
     return a1, a2, info
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K7: INT8 tensor-core exact products (acetn_b200/csrc/i8crt.cu)
+class I8Encoded:
+    """A big FP64 matrix encoded once as 16 planes of int8 residues (+ row/column exponents); opaque device storage."""
+
+    def __init__(self, storage, rows, cols):
+        self.storage, self.rows, self.cols = storage, rows, cols
+
+
+def i8_supported(rows, cols, q):
+    return bool(_lib.load().acetn_b200_i8_supported(rows, cols, q))
+
+
+def i8_encode(Q, stream=None, storage=None):
+    dev = _require_cuda(Q)
+    assert Q.dim() == 2 and Q.stride(1) == 1
+    rows, cols = Q.shape
+    lib = _lib.load()
+    nb = lib.acetn_b200_i8_encoded_bytes(rows, cols)
+    if storage is None or storage.numel() < nb:
+        storage = torch.empty(nb, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_i8_encode(_p(Q), rows, cols, Q.stride(0), _p(storage), storage.numel(), _stream(dev, stream))
+    _lib.check(st, "i8_encode")
+    return I8Encoded(storage, rows, cols)
+
+
+def i8_matmul(enc, Y, adjoint=False, stream=None, out=None):
+    """out = Q @ Y (adjoint=False) or Q.T @ Y (adjoint=True) for an I8Encoded Q; FP64 in/out, integer arithmetic inside."""
+    dev = _require_cuda(Y)
+    Y = Y.contiguous()
+    k, q = Y.shape
+    m = enc.cols if adjoint else enc.rows
+    if k != (enc.rows if adjoint else enc.cols):
+        raise ValueError("i8_matmul: inner dimensions differ")
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(m, q, dtype=torch.float64, device=dev)
+    nb = lib.acetn_b200_i8_matmul_workspace_bytes(enc.rows, enc.cols, q)
+    ws = _ws(dev, nb, stream)
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_i8_matmul(_p(enc.storage), enc.rows, enc.cols, 1 if adjoint else 0, _p(Y), q, q, _p(out), out.stride(0),
+                                      _p(ws), ws.numel(), _stream(dev, stream))
+    _lib.check(st, "i8_matmul")
+    return out

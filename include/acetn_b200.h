@@ -143,6 +143,40 @@ int acetn_b200_double_layer(const double* X, int64_t n0, int64_t n1, int64_t in_
                             int64_t d, double* Y, int64_t out_s0, int64_t out_s1, const int64_t* out_es, void* ws,
                             size_t ws_bytes, void* stream);
 
+/* ---- K7: FP64-exact "big x thin" products on the INT8 tensor cores (tcgen05.mma kind::i8 + TMEM + TMA) --------------
+ *   The thin products of the rSVD chain and of the projector formation (fused_matmul_svd_lowrank.py:33-46,
+ *   projectors.py:166-172; `A @ (B @ omega)` etc. in the reference) multiply the same quarter tensors 13 times per
+ *   site-move.  i8_encode turns a matrix Q (rows x cols) once into 16 planes of int8 residues (two-sided power-of-two
+ *   scaling to 54-bit integers, then mod 16 coprime moduli <= 256); i8_matmul evaluates  out = Q Y  (adjoint = 0, Y: cols x q)
+ *   or  out = Q^T Y  (adjoint = 1, Y: rows x q) exactly in integer arithmetic (one INT8 tensor-core GEMM per modulus,
+ *   Chinese-remainder reconstruction in 128-bit integers) -- the only rounding is the 2^-54 scaling of the operands, so the
+ *   result carries FP64-level error (acetn_b200/csrc/i8crt.cu).  q <= 272; 128 <= rows, cols <= 65535.
+ *   storage (device, acetn_b200_i8_encoded_bytes) is caller-owned and opaque. */
+int acetn_b200_i8_supported(int64_t rows, int64_t cols, int64_t q);
+size_t acetn_b200_i8_encoded_bytes(int64_t rows, int64_t cols);
+int acetn_b200_i8_encode(const double* Q, int64_t rows, int64_t cols, int64_t ldq, void* storage, size_t storage_bytes,
+                         void* stream);
+size_t acetn_b200_i8_matmul_workspace_bytes(int64_t rows, int64_t cols, int64_t q);
+int acetn_b200_i8_matmul(const void* storage, int64_t rows, int64_t cols, int adjoint, const double* Y, int64_t q,
+                         int64_t ldy, double* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+
+/* rSVD / projector formation with K7: encs[i] (or enc1 / enc4) is the acetn_b200_i8_encode storage of factor i, or NULL to
+ * keep that factor on the FP64 DMMA path; mats[i] (Q1 / Q4) may be NULL where an encoding is given.  use_enc[i] != 0 in the
+ * workspace queries marks the encoded factors.  Everything else as acetn_b200_rsvd / acetn_b200_projectors_from_usv. */
+size_t acetn_b200_rsvd_enc_workspace_bytes(int nmat, const int64_t* rows, const int64_t* cols, int64_t q,
+                                           const int32_t* use_enc);
+int acetn_b200_rsvd_enc(int nmat, const double* const* mats, const void* const* encs, const int64_t* rows,
+                        const int64_t* cols, const double* Omega, int64_t q, int niter, int reorth_adjoint, int64_t chi,
+                        double cutoff, double* U, double* S, double* V, int32_t* info, double* AtQ, double* Wt, void* ws,
+                        size_t ws_bytes, void* stream);
+size_t acetn_b200_projectors_enc_workspace_bytes(int64_t m1, int64_t n1, int64_t m4, int64_t n4, int64_t keep,
+                                                 int use_enc);
+int acetn_b200_projectors_from_usv_enc(const double* Q1, const void* enc1, int64_t m1, int64_t n1, const double* Q4,
+                                       const void* enc4, int64_t m4, int64_t n4, const double* U, int64_t ldu,
+                                       const double* V, int64_t ldv, const double* S, int64_t keep, const double* qmax1,
+                                       const double* qmax4, const double* AtQ, const double* Wt, int64_t q,
+                                       double* proj1, double* proj2, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- bench-only: launches a register-resident DMMA.8x8x4 loop on every SM and returns its flop count; timed by the
  *      caller with CUDA events it gives the live FP64 tensor-pipe roof used as the roofline denominator ---------- */
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream);
