@@ -16,6 +16,7 @@ class CTMRGConfig:          # ipeps_config.py:16-24
     rsvd_niter: int = 2
     rsvd_oversampling: int = 2
     disable_progressbar: bool = True
+    thin_engine: str = "auto"   # not a reference field: "auto" | "dmma" | "i8" (renormalization.ProjectorCalculator)
 
 
 class SiteTensor:

@@ -156,17 +156,21 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     return S, Wt, Jt, info
 
 
-def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False):
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False, encs=None):
     """Randomized SVD of mats[0] @ ... @ mats[-1] with the caller's test matrix omega (n, q).
     Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps]).
     want_atq=True additionally returns (AtQ, Wt) = (mats[0]^T Q, core left vectors as rows) and want_u=False skips U
-    (then U is None): the half-system projector pipeline needs only AtQ, Wt and V."""
-    dev = _require_cuda(*mats, omega)
-    mats = [m.contiguous() for m in mats]
-    omega = omega.contiguous()
+    (then U is None): the half-system projector pipeline needs only AtQ, Wt and V.
+    encs: optional list (one entry per factor) of I8Encoded / None; an encoded factor's thin products run on the INT8
+    tensor cores (K7) and its FP64 entry in mats may be None."""
     nmat = len(mats)
-    rows = [m.shape[0] for m in mats]
-    cols = [m.shape[1] for m in mats]
+    encs = list(encs) if encs is not None else [None] * nmat
+    live = [m for m in mats if m is not None]
+    dev = _require_cuda(*live, omega)
+    mats = [m.contiguous() if m is not None else None for m in mats]
+    omega = omega.contiguous()
+    rows = [m.shape[0] if m is not None else e.rows for m, e in zip(mats, encs)]
+    cols = [m.shape[1] if m is not None else e.cols for m, e in zip(mats, encs)]
     n, q = omega.shape
     if n != cols[-1]:
         raise ValueError("rsvd: omega rows must equal the column count of the last factor")
@@ -179,38 +183,45 @@ def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, str
     Wt = torch.empty(q, q, dtype=torch.float64, device=dev) if want_atq else None
     info = torch.empty(2, dtype=torch.int32, device=dev)      # written by the library (no torch kernel on another stream)
     r_arr, c_arr = _lib.i64_array(rows), _lib.i64_array(cols)
-    nb = lib.acetn_b200_rsvd_workspace_bytes(nmat, r_arr, c_arr, q)
+    use = (ctypes.c_int32 * nmat)(*[1 if e is not None else 0 for e in encs])
+    nb = lib.acetn_b200_rsvd_enc_workspace_bytes(nmat, r_arr, c_arr, q, use)
     ws = _ws(dev, nb, stream)
-    ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() for t in mats])
+    ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() if t is not None else None for t in mats])
+    eptrs = (ctypes.c_void_p * nmat)(*[e.storage.data_ptr() if e is not None else None for e in encs])
     with torch.cuda.device(dev):
-        st = lib.acetn_b200_rsvd(nmat, ptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
-                                 q if chi is None else int(chi), float(cutoff), _p(U) if want_u else None, _p(S), _p(V), _p(info),
-                                 _p(AtQ) if want_atq else None, _p(Wt) if want_atq else None, _p(ws), ws.numel(),
-                                 _stream(dev, stream))
+        st = lib.acetn_b200_rsvd_enc(nmat, ptrs, eptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
+                                     q if chi is None else int(chi), float(cutoff), _p(U) if want_u else None, _p(S), _p(V), _p(info),
+                                     _p(AtQ) if want_atq else None, _p(Wt) if want_atq else None, _p(ws), ws.numel(),
+                                     _stream(dev, stream))
     _lib.check(st, "rsvd")
     if want_atq:
         return U, S, V, info, AtQ, Wt
     return U, S, V, info
 
 
-def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=None, AtQ=None, Wt=None):
+def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=None, AtQ=None, Wt=None, enc1=None, enc4=None):
     """projectors.py:166-173. Q1 (m1,n1), Q4 (m4,n4), U (m1,q), V (n4,q). Returns proj1 (n1,keep), proj2 (m4,keep).
-    qmax1/qmax4: max|Q| scalars of un-normalised Q1/Q4 (see acetn_b200.h)."""
-    dev = _require_cuda(Q1, Q4, V, S)
-    m1, n1 = Q1.shape
-    m4, n4 = Q4.shape
+    qmax1/qmax4: max|Q| scalars of un-normalised Q1/Q4 (see acetn_b200.h).  enc1/enc4: I8Encoded Q1/Q4 (K7); the FP64
+    tensor of an encoded factor may be None."""
+    dev = _require_cuda(V, S)
+    m1, n1 = Q1.shape if Q1 is not None else (enc1.rows, enc1.cols)
+    m4, n4 = Q4.shape if Q4 is not None else (enc4.rows, enc4.cols)
     lib = _lib.load()
     p1 = torch.empty(n1, keep, dtype=torch.float64, device=dev)
     p2 = torch.empty(m4, keep, dtype=torch.float64, device=dev)
-    nb = lib.acetn_b200_projectors_workspace_bytes(m1, n1, m4, n4, keep)
+    use_enc = enc1 is not None or enc4 is not None
+    nb = lib.acetn_b200_projectors_enc_workspace_bytes(m1, n1, m4, n4, keep, 1 if use_enc else 0)
     ws = _ws(dev, nb, stream)
+
+    def ptr(t):
+        return _p(t) if t is not None else None
+
     with torch.cuda.device(dev):
-        st = lib.acetn_b200_projectors_from_usv(_p(Q1), m1, n1, _p(Q4), m4, n4, _p(U) if U is not None else None,
-                                                U.stride(0) if U is not None else 0, _p(V), V.stride(0), _p(S), keep,
-                                                _p(qmax1) if qmax1 is not None else None, _p(qmax4) if qmax4 is not None else None,
-                                                _p(AtQ) if AtQ is not None else None, _p(Wt) if Wt is not None else None,
-                                                Wt.shape[0] if Wt is not None else 0,
-                                                _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev, stream))
+        st = lib.acetn_b200_projectors_from_usv_enc(ptr(Q1), ptr(enc1.storage) if enc1 is not None else None, m1, n1,
+                                                    ptr(Q4), ptr(enc4.storage) if enc4 is not None else None, m4, n4,
+                                                    ptr(U), U.stride(0) if U is not None else 0, _p(V), V.stride(0), _p(S), keep,
+                                                    ptr(qmax1), ptr(qmax4), ptr(AtQ), ptr(Wt), Wt.shape[0] if Wt is not None else 0,
+                                                    _p(p1), _p(p2), _p(ws), ws.numel(), _stream(dev, stream))
     _lib.check(st, "projectors_from_usv")
     return p1, p2
 

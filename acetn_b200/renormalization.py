@@ -26,6 +26,11 @@ class ProjectorCalculator:
         self.rsvd_niter = config.rsvd_niter
         self.rsvd_oversampling = config.rsvd_oversampling
         self.spectra = None          # optional recorder: list receiving the normalised spectrum of every projector
+        # engine of the rSVD / projector "big x thin" products: "dmma" = FP64 DMMA GEMM (K1); "i8" = exact integer products on
+        # the INT8 tensor cores (K7, tcgen05); "auto" = K7 when the quarter tensors are large enough to pay for the encoding
+        self.thin_engine = os.environ.get("ACETN_B200_THIN_ENGINE", getattr(config, "thin_engine", "auto"))
+        if self.thin_engine not in ("auto", "dmma", "i8"):
+            raise ValueError(f"Invalid thin_engine: {self.thin_engine} provided.")
         self.set_calculate()
 
     def set_calculate(self):
@@ -49,6 +54,19 @@ class ProjectorCalculator:
         ek1 = site_tensor['E'][(3 + k) % 4]
         ek2 = site_tensor['E'][(0 + k) % 4]
         return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax)
+
+    I8_MIN_DIM = 4096        # "auto": quarter tensors at least this large go through K7
+
+    def _use_i8(self, mats_shapes, q):
+        """True when every factor's thin products should run on the INT8 tensor cores (K7)."""
+        if self.thin_engine == "dmma":
+            return False
+        ok = all(ops.i8_supported(r, c, q) for r, c in mats_shapes)
+        if self.thin_engine == "i8":
+            if not ok:
+                raise RuntimeError(f"thin_engine='i8': shapes {mats_shapes} with q={q} are outside the INT8 engine's range")
+            return True
+        return ok and all(min(r, c) >= self.I8_MIN_DIM for r, c in mats_shapes)
 
     def _check_svd_type(self):
         if self.svd_type not in ("rsvd", "full-rank"):
@@ -124,11 +142,15 @@ class ProjectorCalculator:
         mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
         Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=stream, absmax=mx[0:1])
         Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=stream, absmax=mx[1:2])
+        encs = None
+        if self._use_i8([tuple(Q1.shape), tuple(Q4.shape)], omega.shape[1]):
+            # K7: both quarter tensors are encoded once (16 int8 residue planes) and serve all 13 thin products
+            encs = [ops.i8_encode(Q1, stream=stream), ops.i8_encode(Q4, stream=stream)]
         # U is never materialised: proj1 = Q1^T U = (Q1^T Qy) U_B reuses the first product of the final adjoint pass
         _, S, V, info, AtQ, Wt = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi,
-                                          cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True)
+                                          cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True, encs=encs)
         return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": None, "S": S, "V": V, "info": info,
-                "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream}
+                "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream, "encs": encs}
 
     def begin_full_system(self, ipeps, sites, k, stream=None, omega=None):
         """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
@@ -143,10 +165,13 @@ class ProjectorCalculator:
         Q2, _ = self.make_quarter_tensor(ipeps[s2], k + 1, normalize=True, stream=stream)
         Q3, _ = self.make_quarter_tensor(ipeps[s3], k + 2, normalize=True, stream=stream)
         Q4, q4D = self.make_quarter_tensor(ipeps[s4], k + 3, normalize=True, stream=stream)
+        encs = None
+        if self._use_i8([tuple(Q.shape) for Q in (Q2, Q1, Q4, Q3)], omega.shape[1]):
+            encs = [ops.i8_encode(Q, stream=stream) for Q in (Q2, Q1, Q4, Q3)]
         U, S, V, info = ops.rsvd([Q2, Q1, Q4, Q3], omega, niter=self.rsvd_niter, reorth_adjoint=True, chi=chi,
-                                 cutoff=self.svd_cutoff, stream=stream)
+                                 cutoff=self.svd_cutoff, stream=stream, encs=encs)
         return {"kind": "full", "Q1": Q1, "Q2": Q2, "Q3": Q3, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": U, "S": S, "V": V,
-                "info": info, "omega": omega, "stream": stream}
+                "info": info, "omega": omega, "stream": stream, "encs": encs}
 
     def draw_omega(self, ipeps, sites, k):
         """The Gaussian test matrix of this projector, drawn exactly where/how the reference draws it
@@ -184,16 +209,23 @@ class ProjectorCalculator:
         q1D, q4D = pend["q1D"], pend["q4D"]
         if pend["kind"] == "half":
             mx = pend["mx"]
+            encs = pend.get("encs")
             p1, p2 = ops.projectors_from_usv(pend["Q1"], pend["Q4"], None, pend["V"], S, keep, stream=stream,
-                                             qmax1=mx[0:1], qmax4=mx[1:2], AtQ=pend["AtQ"], Wt=pend["Wt"])
+                                             qmax1=mx[0:1], qmax4=mx[1:2], AtQ=pend["AtQ"], Wt=pend["Wt"],
+                                             enc4=encs[1] if encs is not None else None)
         else:
             # projectors.py:209-217 : proj1 = Q1^H (Q2^H conj(U)), proj2 = Q4 (Q3 V), columns scaled by s^-1/2
             # (runs on the main stream; finish() already synchronised the side stream)
             w = 1.0 / torch.sqrt(S[:keep] / S[0])
             Us = (pend["U"][:, :keep] * w).contiguous()
             Vs = (pend["V"][:, :keep] * w).contiguous()
-            p1 = ops.matmul(pend["Q1"], ops.matmul(pend["Q2"], Us, transpose_a=True), transpose_a=True)
-            p2 = ops.matmul(pend["Q4"], ops.matmul(pend["Q3"], Vs))
+            encs = pend.get("encs")
+            if encs is not None and keep >= 1:
+                p1 = ops.i8_matmul(encs[1], ops.i8_matmul(encs[0], Us, adjoint=True), adjoint=True)
+                p2 = ops.i8_matmul(encs[2], ops.i8_matmul(encs[3], Vs))
+            else:
+                p1 = ops.matmul(pend["Q1"], ops.matmul(pend["Q2"], Us, transpose_a=True), transpose_a=True)
+                p2 = ops.matmul(pend["Q4"], ops.matmul(pend["Q3"], Vs))
         return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
 
     def calculate_half_system(self, ipeps, sites, k):
