@@ -9,10 +9,10 @@
 //        a'_ij = rint(Q_ij 2^(P - r_i - c_j)),   b'_jz = rint(Y_jz 2^(c_j) 2^(P - e_z))       (|a'|,|b'| <= 2^P)
 //      r_i / c_j = row / column binary exponents of Q (c_j taken after the row scaling), e_z = column exponent of the
 //      row-shifted Y.  The only rounding of the whole product happens here: 2^-54 relative to the row/column scale.
-//   2. a', b' are reduced modulo 16 pairwise coprime moduli m_l <= 256 (balanced residues, int8): one pass over Q per
-//      site-move (i8_encode), one cheap pass over each thin operand.
-//   3. per modulus an exact INT8 x INT8 -> INT32 GEMM on the tensor cores (k * 2^14 < 2^31), epilogue reduces the
-//      accumulator mod m_l back to int8.
+//   2. a', b' are reduced modulo 16 pairwise coprime moduli m_l <= 256 (a': residues in [0,m) as uint8, b': balanced
+//      residues as int8): one pass over Q per site-move (i8_encode), one cheap pass over each thin operand.
+//   3. per modulus an exact UINT8 x INT8 -> INT32 GEMM on the tensor cores (k * 255 * 128 < 2^31 for k <= 65535), epilogue
+//      reduces the accumulator mod m_l back to int8.
 //   4. Chinese remainder reconstruction in 128-bit integer arithmetic: x = sum_l t_l W_l - round(sum_l t_l/m_l) M is the
 //      exact integer sum_j a'_ij b'_jz because |x| <= k 2^(2P) < M/4 (M = prod m_l ~ 2^125.4);  D_iz = x 2^(r_i + e_z - 2P).
 //
@@ -21,6 +21,7 @@
 // accumulators in TMEM), warps 2-5 = epilogue (tcgen05.ld -> mod m_l -> int8 store).  The adjoint product reads the SAME
 // residue planes through an MN-major shared-memory descriptor, so Q is encoded once for Q Y and Q^T Y.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "crt_tables.h"
 #include "i8crt.cuh"
@@ -35,6 +36,9 @@ __constant__ float c_inv[I8_NMOD] = CRT_INV_INIT;
 __constant__ int c_qinv[I8_NMOD] = CRT_QINV_INIT;
 __constant__ uint32_t c_p256lo[I8_NMOD] = CRT_P256_LO_INIT;
 __constant__ uint32_t c_p256hi[I8_NMOD] = CRT_P256_HI_INIT;
+__constant__ int c_off0[I8_NMOD] = CRT_OFF0_INIT;
+__constant__ int c_off1[I8_NMOD] = CRT_OFF1_INIT;
+__constant__ uint32_t c_magic[I8_NMOD] = CRT_MAGIC_INIT;
 __constant__ unsigned long long c_wlo[I8_NMOD] = CRT_W_LO_INIT;
 __constant__ unsigned long long c_whi[I8_NMOD] = CRT_W_HI_INIT;
 
@@ -68,16 +72,18 @@ __device__ __forceinline__ long long scaled_int(double x, int shift) {
     long long v = __double2ll_rn(__longlong_as_double(mag));
     return bits < 0 ? -v : v;
 }
-// 16 balanced residues of v
-__device__ __forceinline__ void residues16(long long v, int r[I8_NMOD]) {
-    unsigned long long a = (unsigned long long)(v < 0 ? -v : v);
-    uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+// 16 residues of v (|v| <= 2^55) in [0, m_l).  The eight bytes of the two's-complement representation are reduced with two
+// dp4a against 256^b mod m (signed bytes); the accumulator starts at a multiple of m that keeps the sum positive (and, for
+// negative v, removes 2^64 mod m); floor division by the 32-bit reciprocal is exact for sums < 2^20.
+__device__ __forceinline__ void residues16u(long long v, int r[I8_NMOD]) {
+    const unsigned long long u = (unsigned long long)v;
+    const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+    const bool neg = v < 0;
 #pragma unroll
     for (int l = 0; l < I8_NMOD; l++) {
-        int s = dp4a_us(lo, c_p256lo[l], 0);
-        s = dp4a_us(hi, c_p256hi[l], s);
-        if (v < 0) s = -s;
-        r[l] = bal_mod(s, c_mod[l], c_lo[l], c_inv[l]);
+        int s = dp4a_us(hi, c_p256hi[l], neg ? c_off1[l] : c_off0[l]);
+        s = dp4a_us(lo, c_p256lo[l], s);
+        r[l] = s - (int)__umulhi((uint32_t)s, c_magic[l]) * c_mod[l];
     }
 }
 
@@ -121,34 +127,47 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) encode_big_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
                                                          const int32_t* __restrict__ rowexp, const int32_t* __restrict__ colexp, int P,
-                                                         int8_t* __restrict__ res, int64_t ld) {
+                                                         int8_t* __restrict__ res, int64_t ld, int vec_ok) {
     const int64_t i = blockIdx.y;
     const int64_t j0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
     if (j0 >= ld) return;
     const int re = rowexp[i];
+    double x[8];
+    int ce[8];
+    if (vec_ok && j0 + 8 <= cols) {
+        const double2* src = reinterpret_cast<const double2*>(Q + i * ldq + j0);
+        const int4* csrc = reinterpret_cast<const int4*>(colexp + j0);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { double2 t = __ldcs(src + c); x[2 * c] = t.x; x[2 * c + 1] = t.y; }
+        int4 c0 = __ldg(csrc), c1 = __ldg(csrc + 1);
+        ce[0] = c0.x; ce[1] = c0.y; ce[2] = c0.z; ce[3] = c0.w; ce[4] = c1.x; ce[5] = c1.y; ce[6] = c1.z; ce[7] = c1.w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int64_t j = j0 + c;
+            x[c] = j < cols ? Q[i * ldq + j] : 0.0;
+            ce[c] = j < cols ? colexp[j] : EXP_NONE;
+        }
+    }
     uint32_t w0[I8_NMOD], w1[I8_NMOD];
 #pragma unroll
     for (int l = 0; l < I8_NMOD; l++) { w0[l] = 0; w1[l] = 0; }
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        const int64_t j = j0 + c;
         long long v = 0;
-        if (j < cols && re > EXP_NONE) {
-            int ce = colexp[j];
-            if (ce > EXP_NONE) v = scaled_int(Q[i * ldq + j], P - re - ce);
-        }
+        if (re > EXP_NONE && ce[c] > EXP_NONE) v = scaled_int(x[c], P - re - ce[c]);
         int r[I8_NMOD];
-        residues16(v, r);
+        residues16u(v, r);
 #pragma unroll
         for (int l = 0; l < I8_NMOD; l++) {
-            uint32_t b = (uint32_t)(r[l] & 0xff) << (8 * (c & 3));
-            if (c < 4) w0[l] |= b; else w1[l] |= b;
+            if (c < 4) w0[l] |= (uint32_t)r[l] << (8 * (c & 3));
+            else w1[l] |= (uint32_t)r[l] << (8 * (c & 3));
         }
     }
     const int64_t plane = rows * ld;
 #pragma unroll
     for (int l = 0; l < I8_NMOD; l++)
-        *reinterpret_cast<uint2*>(res + l * plane + i * ld + j0) = make_uint2(w0[l], w1[l]);
+        __stcs(reinterpret_cast<uint2*>(res + l * plane + i * ld + j0), make_uint2(w0[l], w1[l]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -199,10 +218,11 @@ __global__ void __launch_bounds__(256) thin_encode_kernel(const double* __restri
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             int r[I8_NMOD];
-            residues16(sv[tz][jb + c], r);
+            residues16u(sv[tz][jb + c], r);
 #pragma unroll
             for (int l = 0; l < I8_NMOD; l++) {
-                uint32_t b = (uint32_t)(r[l] & 0xff) << (8 * (c & 3));
+                const int rb = r[l] > c_lo[l] + c_mod[l] - 1 ? r[l] - c_mod[l] : r[l];      // balanced: the B operand is signed
+                uint32_t b = (uint32_t)(rb & 0xff) << (8 * (c & 3));
                 if (c < 4) w0[l] |= b; else w1[l] |= b;
             }
         }
@@ -246,7 +266,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], s8 x s8 -> s32
+// D[tmem] (+)= A[smem] * B[smem], u8 x s8 -> s32
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -272,9 +292,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= 2ull << 61;                         // LayoutType::SWIZZLE_128B
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): s32 accumulate, s8 x s8, M = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor): s32 accumulate, A = u8 (residues in [0,m)), B = s8 (balanced), M = 128
 __host__ __device__ constexpr uint32_t i8_idesc(int n, int a_mn_major) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct GemmParams {
@@ -414,6 +434,182 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair version (tcgen05.mma.cta_group::2, M = 256 over two SMs of a TPC) -- experimental, opt-in (see i8_pair_mode).
+// Per 128-deep K block the single-CTA kernel writes 50 KB by TMA and the tensor core reads A twice (N = 128 + 144) plus the
+// whole B tile.  In pair mode each CTA stages its own 128 A rows and only HALF of the B tile (the MMA reads the other half
+// from the peer SM), so TMA writes drop to 33 KB and operand reads by a quarter.  Measured: no gain (the IMMA pipe, 70 %
+// active under the power cap, is the limiter, not shared memory).
+//   * both CTAs issue cp.async.bulk.tensor...cta_group::2 loads whose complete_tx lands on the LEADER's (rank 0) full barrier;
+//   * the leader's elected thread issues the MMAs and multicasts tcgen05.commit to the empty / tmem_full barriers of both CTAs;
+//   * each CTA drains its own 128 TMEM lanes; the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(leader_bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t i8_idesc_pair(int n, int a_mn_major) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                    const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
+    const uint32_t bar_tmem_full = bar_base + 16u * (uint32_t)p.stages;
+    const uint32_t bar_tmem_empty = bar_tmem_full + 8;
+    const uint32_t tmem_holder = bar_tmem_empty + 8;
+    uint32_t* tmem_holder_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int h1 = p.n1 >> 1, h2 = p.n2 >> 1;          // B rows of each MMA staged by this CTA
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(bar_base + 16u * s, 1);           // full: the leader's arrive.expect_tx (bytes of both CTAs)
+            mbar_init(bar_base + 16u * s + 8, 1);       // empty: one multicast tcgen05.commit
+        }
+        mbar_init(bar_tmem_full, 1);
+        mbar_init(bar_tmem_empty, 8);                   // 4 epilogue warps x 2 CTAs (used on the leader only)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_holder), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+    const int total = I8_NMOD * p.mtiles;               // mtiles counts 256-row tiles here
+    const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs) =====
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx_pair = 2u * (uint32_t)(A_TILE_BYTES + (h1 + h2) * 128);
+            for (int item = pair; item < total; item += npairs) {
+                const int l = item / p.mtiles, mt = item - l * p.mtiles;
+                const int m0 = mt * 256 + (int)rank * 128;
+                for (int kc = 0; kc < p.nk; kc++) {
+                    const uint32_t full = bar_base + 16u * s, empty = full + 8;
+                    const uint32_t full_leader = mapa_rank(full, 0);
+                    mbar_wait(empty, ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(full, tx_pair);
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    if (!p.trans) tma_load_3d_2sm(sa, &tmA, full_leader, kc * 128, m0, l);
+                    else tma_load_3d_2sm(sa, &tmA, full_leader, m0, kc * 128, l);
+                    tma_load_3d_2sm(sa + A_TILE_BYTES, &tmB1, full_leader, kc * 128, (int)rank * h1, l);
+                    if (h2 > 0) tma_load_3d_2sm(sa + A_TILE_BYTES + (uint32_t)(h1 * 128), &tmB2, full_leader, kc * 128, p.n1 + (int)rank * h2, l);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            const uint32_t idesc1 = i8_idesc_pair(p.n1, p.trans);
+            const uint32_t idesc2 = i8_idesc_pair(p.n2 > 0 ? p.n2 : 32, p.trans);
+            const uint32_t a_kstep = p.trans ? (32u * 128u) >> 4 : 32u >> 4;
+            int s = 0;
+            uint32_t ph = 0, tph = 0;
+            for (int item = pair; item < total; item += npairs) {
+                mbar_wait(bar_tmem_empty, tph ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < p.nk; kc++) {
+                    const uint32_t full = bar_base + 16u * s, empty = full + 8;
+                    mbar_wait(full, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    const uint32_t sb = sa + A_TILE_BYTES;
+                    const uint64_t da = smem_desc(sa, p.trans ? 16384u : 16u, 1024u);
+                    const uint64_t db1 = smem_desc(sb, 16u, 1024u);
+                    const uint64_t db2 = smem_desc(sb + (uint32_t)h1 * 128u, 16u, 1024u);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        const uint32_t acc = (kc | k4) != 0;
+                        tc_mma_i8_pair(tmem_base, da + (uint64_t)(a_kstep * k4), db1 + (uint64_t)(2 * k4), idesc1, acc);
+                        if (p.n2 > 0)
+                            tc_mma_i8_pair(tmem_base + (uint32_t)p.n1, da + (uint64_t)(a_kstep * k4), db2 + (uint64_t)(2 * k4), idesc2, acc);
+                    }
+                    tc_commit_pair(empty);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+                tc_commit_pair(bar_tmem_full);
+                tph ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own 128 TMEM lanes) =====
+        const int quarter = warp & 3;
+        const uint32_t tmem_empty_leader = mapa_rank(bar_tmem_empty, 0);
+        uint32_t tph = 0;
+        for (int item = pair; item < total; item += npairs) {
+            const int l = item / p.mtiles, mt = item - l * p.mtiles;
+            const int m = c_mod[l], lo = c_lo[l];
+            const float inv = c_inv[l];
+            mbar_wait(bar_tmem_full, tph);
+            tc_fence_after();
+            const int64_t row = (int64_t)mt * 256 + (int64_t)rank * 128 + quarter * 32 + lane;
+            int8_t* orow = p.out + ((int64_t)l * p.m_out + row) * p.npad;
+            for (int c0 = 0; c0 < p.npad; c0 += 16) {
+                uint32_t v[16];
+                tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    int r = bal_mod((int)v[c], m, lo, inv);
+                    w[c >> 2] |= (uint32_t)(r & 0xff) << (8 * (c & 3));
+                }
+                if (row < p.m_out) *reinterpret_cast<uint4*>(orow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+            tph ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // CRT reconstruction.  Thread = 4 consecutive columns of one output row.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ res, int64_t m, int npad, int q, const int32_t* __restrict__ erow,
@@ -535,7 +731,8 @@ int i8_encode_launch(const double* Q, int64_t rows, int64_t cols, int64_t ldq, v
     AB_LAUNCHED();
     col_exp_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)((rows + 63) / 64)), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp);
     AB_LAUNCHED();
-    encode_big_kernel<<<dim3((unsigned)((ld / 8 + 255) / 256), (unsigned)rows), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld);
+    const int vec_ok = (ldq % 2 == 0) && (((uintptr_t)Q & 15) == 0) && (((uintptr_t)colexp & 15) == 0);
+    encode_big_kernel<<<dim3((unsigned)((ld / 8 + 255) / 256), (unsigned)rows), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld, vec_ok);
     AB_LAUNCHED();
     enc->res = res; enc->rowexp = rowexp; enc->colexp = colexp; enc->rows = rows; enc->cols = cols; enc->ld = ld; enc->P = P;
     return OK;
@@ -553,35 +750,73 @@ int i8_thin_encode_launch(const double* Y, int64_t k, int64_t q, int64_t ldy, co
     return OK;
 }
 
+// 0 = single-CTA kernel (default), 1 = CTA-pair kernel; ACETN_B200_I8_PAIR=1 opts in (read once).
+// EXPERIMENTAL: the pair kernel is bit-exact in isolation (tools/i8_check.py, all GPU tests) but measured no faster (1.19 vs
+// 1.18 ms per thin product: the INT8 pipe is clock/power bound, not shared-memory bound), and bench.py, which runs four
+// projector tasks on four streams, hung with it -- unresolved, hence never selected by default.
+int i8_pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("ACETN_B200_I8_PAIR");
+        mode = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return mode;
+}
+
 int i8_gemm_launch(const int8_t* Ares, int64_t rows, int64_t cols, int64_t ld, bool adjoint, const int8_t* Bres, int64_t ldk, int npad,
                    int8_t* Cres, cudaStream_t s) {
     AB_REQUIRE(npad % 16 == 0 && npad >= 16 && npad <= I8_MAX_THIN, "i8_gemm: npad must be a multiple of 16 in [16, %d]", I8_MAX_THIN);
     const int64_t m_out = adjoint ? cols : rows, kdim = adjoint ? rows : cols;
-    AB_REQUIRE(kdim <= 65536, "i8_gemm: contraction length %lld exceeds the INT32 accumulator bound", (long long)kdim);
+    AB_REQUIRE(kdim <= 65535, "i8_gemm: contraction length %lld exceeds the INT32 accumulator bound", (long long)kdim);
+    const bool pair = i8_pair_mode() != 0 && m_out > 128;
     GemmParams p;
-    p.out = Cres; p.m_out = m_out; p.mtiles = (int)((m_out + 127) / 128); p.nk = (int)((kdim + 127) / 128); p.trans = adjoint ? 1 : 0;
+    p.out = Cres; p.m_out = m_out; p.nk = (int)((kdim + 127) / 128); p.trans = adjoint ? 1 : 0;
     p.npad = npad;
-    if (npad <= 256) { p.n1 = npad; p.n2 = 0; p.b_box_rows = npad; p.b_loads = 1; }
-    else { p.n1 = 128; p.n2 = npad - 128; p.b_box_rows = npad / 2; p.b_loads = 2; }
-    p.stage_bytes = A_TILE_BYTES + npad * 128;
-    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+    const int sms = device_sm_count();
     const int smem_budget = 227 * 1024 - 1024 - 256;
+    CUtensorMap tmA, tmB, tmB2;
+    AB_TRY(make_map(&tmA, Ares, cols, rows, ld, I8_NMOD, 128));
+    if (!pair) {
+        p.mtiles = (int)((m_out + 127) / 128);
+        if (npad <= 256) { p.n1 = npad; p.n2 = 0; p.b_box_rows = npad; p.b_loads = 1; }
+        else { p.n1 = 128; p.n2 = npad - 128; p.b_box_rows = npad / 2; p.b_loads = 2; }
+        p.stage_bytes = (A_TILE_BYTES + npad * 128 + 1023) / 1024 * 1024;
+        p.stages = smem_budget / p.stage_bytes;
+        if (p.stages > 8) p.stages = 8;
+        AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
+        const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
+        AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
+        static size_t smem_set = 0;
+        if (smem_bytes > smem_set) {
+            AB_CHECK_CUDA(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            smem_set = smem_bytes;
+        }
+        int grid = I8_NMOD * p.mtiles;
+        if (grid > sms) grid = sms;
+        i8_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, p);
+        AB_LAUNCHED();
+        return OK;
+    }
+    // CTA pair: 256-row tiles; every MMA's N is a multiple of 16 so that each CTA stages N/2 (a multiple of 8) B rows
+    p.mtiles = (int)((m_out + 255) / 256);
+    if (npad <= 256) { p.n1 = npad; p.n2 = 0; }
+    else { p.n1 = 128; p.n2 = npad - 128; }
+    AB_REQUIRE(p.n1 % 16 == 0 && p.n2 % 16 == 0, "i8_gemm: pair mode needs N halves that are multiples of 8");
+    p.b_box_rows = p.n1 / 2; p.b_loads = p.n2 > 0 ? 2 : 1;
+    p.stage_bytes = (A_TILE_BYTES + (npad / 2) * 128 + 1023) / 1024 * 1024;
     p.stages = smem_budget / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
-    AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
-    CUtensorMap tmA, tmB;
-    AB_TRY(make_map(&tmA, Ares, cols, rows, ld, I8_NMOD, 128));
-    AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
-    static size_t smem_set = 0;
-    if (smem_bytes > smem_set) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        smem_set = smem_bytes;
+    AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.n1 / 2));
+    AB_TRY(make_map(&tmB2, Bres, kdim, npad, ldk, I8_NMOD, p.n2 > 0 ? p.n2 / 2 : 8));
+    static size_t smem_set2 = 0;
+    if (smem_bytes > smem_set2) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        smem_set2 = smem_bytes;
     }
-    int grid = I8_NMOD * p.mtiles;
-    const int sms = device_sm_count();
-    if (grid > sms) grid = sms;
-    i8_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, p);
+    int pairs = I8_NMOD * p.mtiles;
+    if (pairs > sms / 2) pairs = sms / 2;
+    i8_gemm_pair_kernel<<<2 * pairs, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, tmB2, p);
     AB_LAUNCHED();
     return OK;
 }

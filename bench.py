@@ -273,27 +273,26 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (K1 thin DGEMM, 14 launches per site-move, 2/3 of the sweep's flops) ----
+        # ---- rooflines, measured live (CUDA events on the launching stream; operands of 2 GiB+ exceed L2) --------------
+        import ctypes
         m = chi * D * D
         q = chi + 2
-        st = ip[(0, 0)]
-        Q, _ = ops.quarter_tensor(st['C'][0], st['E'][0], st['E'][3], st['A'])
-        X = torch.randn(m, q, dtype=torch.float64, device=dev)
-        for _ in range(3):
-            ops.matmul(Q, X)
-        torch.cuda.synchronize()
         nrep = 20
-        e0.record()
-        for _ in range(nrep):
-            ops.matmul(Q, X)            # Q (2 GiB at D=8 chi=256) exceeds L2, no flush needed
-        e1.record()
-        torch.cuda.synchronize()
-        t_gemm = e0.elapsed_time(e1) / nrep * 1e-3
-        achieved = 2.0 * m * m * q / t_gemm * 1e-12
         lib = _lib.load()
-        scratch = torch.empty(1 << 20, dtype=torch.float64, device=dev)
-        import ctypes
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(nrep):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / nrep * 1e-3
+
+        scratch = torch.empty(1 << 20, dtype=torch.float64, device=dev)
         lib.acetn_b200_fp64_peak_probe(ctypes.c_void_p(scratch.data_ptr()), 2000, stream)
         torch.cuda.synchronize()
         e0.record()
@@ -301,20 +300,63 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
         peak = fl / (e0.elapsed_time(e1) * 1e-3) * 1e-12
-        traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+        traffic = {}
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))
             except Exception:
-                traffic = None
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "dgemm_dmma_kernel (K1), thin GEMM %dx%dx%d" % (m, q, m),
-                    "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 entry)",
-                    "whole_sweep_tflops": flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n,
-                    # 13 thin DGEMMs per site-move (12 rSVD + proj2), per rank; share = their summed duration / step time
-                    "launches_per_step": 13 * site_moves // n,
-                    "share_of_step": (13 * site_moves / n) * t_gemm / (ms * 1e-3 / args.steps)}
+                traffic = {}
+        step_s = ms * 1e-3 / args.steps
+        st = ip[(0, 0)]
+        Q, _ = ops.quarter_tensor(st['C'][0], st['E'][0], st['E'][3], st['A'])
+        X = torch.randn(m, q, dtype=torch.float64, device=dev)
+        use_i8 = mover.projector_calculator._use_i8([(m, m), (m, m)], q)
+        # K1 (FP64 DMMA GEMM) on the contraction class that dominates its time: (chi D^2) x (chi D^2) x chi, the 2 chi^3 D^4
+        # steps of make_quarter_tensor (projectors.py:53) and renormalize_ej (directional_mover.py:362,365): 4 per site-move
+        Am = torch.randn(m, chi, dtype=torch.float64, device=dev)
+        Bm = torch.randn(chi, m, dtype=torch.float64, device=dev)
+        t_med = timed(lambda: ops.matmul(Am, Bm, out=Q))
+        med_flops = 2.0 * m * m * chi
+        k1 = {"bound": "tensor", "achieved": med_flops / t_med * 1e-12, "peak": peak, "unit": "TFLOP/s",
+              "frac": med_flops / t_med * 1e-12 / peak, "traffic": traffic.get("k1_medium_dram_bytes_per_launch"),
+              "kernel": "dgemm_dmma_kernel (K1), %dx%dx%d (2 chi^3 D^4 contraction class)" % (m, m, chi),
+              "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 entry)",
+              "launches_per_step": 4 * site_moves // n, "share_of_step": (4 * site_moves / n) * t_med / step_s}
+        Q, _ = ops.quarter_tensor(st['C'][0], st['E'][0], st['E'][3], st['A'])
+        del Am, Bm
+        # the thin product (chi D^2)^2 x (chi+2): 13 per site-move.  K1 (DMMA) and, when selected, K7 (INT8 tensor cores, exact)
+        t_thin_dmma = timed(lambda: ops.matmul(Q, X))
+        thin_flops = 2.0 * m * m * q
+        thin = {"dmma_ms": t_thin_dmma * 1e3, "dmma_tflops": thin_flops / t_thin_dmma * 1e-12, "dmma_frac_of_fp64_peak": thin_flops / t_thin_dmma * 1e-12 / peak}
+        roofline = k1
+        k7 = None
+        if use_i8:
+            enc = ops.i8_encode(Q)
+            t_enc = timed(lambda: ops.i8_encode(Q, storage=enc.storage))
+            out = torch.empty(m, q, dtype=torch.float64, device=dev)
+            t_i8 = timed(lambda: ops.i8_matmul(enc, X, out=out))
+            # algorithmic HBM bytes of one K7 product: 16 residue planes of Q (int8) + thin operand in (FP64) + result out (FP64)
+            i8_bytes = 16.0 * m * m + 2.0 * 8.0 * m * q
+            k7 = {"bound": "hbm", "achieved": i8_bytes / t_i8 * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": i8_bytes / t_i8 * 1e-9 / hbm_peak,
+                  "traffic": traffic.get("k7_product_dram_bytes"), "peak_source": hbm_src,
+                  "kernel": "K7 thin product %dx%dx%d = thin_encode + i8_gemm_kernel (tcgen05.mma kind::i8) + crt_kernel" % (m, q, m),
+                  "ms": t_i8 * 1e3, "fp64_equivalent_tflops": thin_flops / t_i8 * 1e-12, "x_fp64_dmma_peak": thin_flops / t_i8 * 1e-12 / peak,
+                  "int8_tops": 16.0 * 2.0 * m * m * (((q + 15) // 16) * 16) / t_i8 * 1e-12,
+                  "encode_ms_per_quarter_tensor": t_enc * 1e3, "encode_gbs": (8.0 + 16.0) * m * m / t_enc * 1e-9,
+                  "launches_per_step": 13 * site_moves // n, "share_of_step": ((13 * t_i8 + 2 * t_enc) * site_moves / n) / step_s}
+            thin["speedup_k7_over_dmma"] = t_thin_dmma / t_i8
+            del enc, out
+        roofline["whole_sweep_tflops"] = flops_sweep(nx, ny, D, chi, d) * args.steps / (ms * 1e-3) * 1e-12 / n
+        roofline["whole_sweep_frac_of_fp64_peak"] = roofline["whole_sweep_tflops"] / peak
+        roofline["thin_product"] = thin
         del Q, X
         ops.release_workspace()
         torch.cuda.empty_cache()
@@ -331,6 +373,9 @@ def run_b200(args):
                            "l2": "inputs (2 GiB quarter tensors) exceed the 126 MB L2; no flush between iterations"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+        line["config"]["thin_engine"] = "i8 (K7: exact integer products on the INT8 tensor cores)" if use_i8 else "dmma (K1)"
+        if k7 is not None:
+            line["roofline_k7"] = k7
         if cpu is not None:
             line["cpu_baseline"] = cpu
 

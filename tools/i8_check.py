@@ -74,7 +74,7 @@ def check_small(rows, cols, q, adjoint, seed, graded=False):
     ld = ld128(cols)
     st = enc.storage.cpu()
     off = 0
-    res = st[off:off + 16 * rows * ld].view(torch.int8).view(16, rows, ld); off += r256(16 * rows * ld)
+    res = st[off:off + 16 * rows * ld].view(16, rows, ld); off += r256(16 * rows * ld)      # uint8: A residues in [0, m)
     rexp = st[off:off + rows * 4].view(torch.int32); off += r256(rows * 4)
     cexp = st[off:off + cols * 4].view(torch.int32)
     e1 = bool((rexp.to(torch.int64) == re).all()); e2 = bool((cexp.to(torch.int64) == ce).all())
@@ -82,7 +82,7 @@ def check_small(rows, cols, q, adjoint, seed, graded=False):
     ok &= e1 and e2
     bad = 0
     for l, m in enumerate(MODS):
-        bad += int((res[l, :, :cols].to(torch.int64) != bal(Ai, m)).sum())
+        bad += int((res[l, :, :cols].to(torch.int64) != torch.remainder(Ai, m)).sum())
         bad += int((res[l, :, cols:] != 0).sum())
     print(tag, "A residues", "PASS" if bad == 0 else f"FAIL ({bad} mismatches)")
     ok &= bad == 0
