@@ -687,6 +687,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int
     return OK;
 }
 inline int npad_of(int64_t q) { return (int)((q + 15) / 16 * 16); }
+inline int env_int(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
 
 }  // namespace
 
@@ -780,9 +781,13 @@ int i8_gemm_launch(const int8_t* Ares, int64_t rows, int64_t cols, int64_t ld, b
         p.mtiles = (int)((m_out + 127) / 128);
         if (npad <= 256) { p.n1 = npad; p.n2 = 0; p.b_box_rows = npad; p.b_loads = 1; }
         else { p.n1 = 128; p.n2 = npad - 128; p.b_box_rows = npad / 2; p.b_loads = 2; }
+        // tuning knobs (dev tools only): ACETN_B200_I8_N1 = columns of the first MMA when the tile needs two, ACETN_B200_I8_STAGES
+        static const int dbg_n1 = env_int("ACETN_B200_I8_N1"), dbg_stages = env_int("ACETN_B200_I8_STAGES");
+        if (p.n2 > 0 && dbg_n1 >= 16 && dbg_n1 <= 256 && dbg_n1 % 16 == 0 && npad - dbg_n1 >= 16) { p.n1 = dbg_n1; p.n2 = npad - dbg_n1; }
         p.stage_bytes = (A_TILE_BYTES + npad * 128 + 1023) / 1024 * 1024;
         p.stages = smem_budget / p.stage_bytes;
         if (p.stages > 8) p.stages = 8;
+        if (dbg_stages >= 2 && dbg_stages < p.stages) p.stages = dbg_stages;
         AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
         const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
         AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
