@@ -357,10 +357,15 @@ int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t i
         configured = true;
     }
     int64_t nblk = n0 * n1;
-    int grid = device_sm_count();
-    if (nblk < grid) grid = (int)nblk;
+    // one CTA per SM is resident at a time; `waves` CTAs per SM in the grid (each stages the site tensor once for >= 64 blocks)
+    // bound the time a higher-priority stream waits for an SM (the rSVD chains of other site tasks, renormalization.py)
+    static const int waves_env = getenv("ACETN_B200_K2_WAVES") ? atoi(getenv("ACETN_B200_K2_WAVES")) : 0;
+    int waves = waves_env > 0 ? waves_env : 4;
+    while (waves > 1 && nblk < (int64_t)device_sm_count() * waves * 64) waves--;
+    int64_t grid = (int64_t)device_sm_count() * waves;
+    if (nblk < grid) grid = nblk;
     if (grid < 1) return OK;
-    double_layer_fused_d8_kernel<<<grid, F_THREADS, FUSED_SMEM, s>>>(p);
+    double_layer_fused_d8_kernel<<<(unsigned)grid, F_THREADS, FUSED_SMEM, s>>>(p);
     AB_LAUNCHED();
     return OK;
 }

@@ -129,8 +129,12 @@ class ProjectorCalculator:
         return self._full_rank_projectors(R1, R2, F, d1, d4, ipeps.dims["chi"])
 
     # ---- phase 1 ------------------------------------------------------------------------------------------------
-    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None):
-        """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed)."""
+    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None):
+        """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed).
+        bulk: optional second CUDA stream for the throughput-bound first stage (quarter tensors + their K7 encodings); the rSVD
+        chain (K7 products interleaved with ~500 latency-bound TSQR / Jacobi launches) then runs on `stream`, ordered behind
+        the first stage by an event.  DirectionalMover.move_pair passes one low-priority bulk stream for all tasks of a phase
+        and a high-priority `stream` per task."""
         self._check_svd_type()
         if self.svd_type == "full-rank":
             return {"kind": "done", "result": self._full_rank_half_system(ipeps, sites, k), "stream": None}
@@ -139,20 +143,25 @@ class ProjectorCalculator:
         chi = ipeps.dims["chi"]
         if omega is None:
             omega = self.draw_omega(ipeps, sites, k)
+        sa = bulk if (bulk is not None and stream is not None) else stream
         mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
-        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=stream, absmax=mx[0:1])
-        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=stream, absmax=mx[1:2])
+        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1])
+        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2])
         encs = None
         if self._use_i8([tuple(Q1.shape), tuple(Q4.shape)], omega.shape[1]):
             # K7: both quarter tensors are encoded once (16 int8 residue planes) and serve all 13 thin products
-            encs = [ops.i8_encode(Q1, stream=stream), ops.i8_encode(Q4, stream=stream)]
+            encs = [ops.i8_encode(Q1, stream=sa), ops.i8_encode(Q4, stream=sa)]
+        if sa is not stream:
+            built = torch.cuda.Event()
+            built.record(sa)
+            stream.wait_event(built)
         # U is never materialised: proj1 = Q1^T U = (Q1^T Qy) U_B reuses the first product of the final adjoint pass
         _, S, V, info, AtQ, Wt = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi,
                                           cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True, encs=encs)
         return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": None, "S": S, "V": V, "info": info,
                 "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream, "encs": encs}
 
-    def begin_full_system(self, ipeps, sites, k, stream=None, omega=None):
+    def begin_full_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None):
         """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
         self._check_svd_type()
         if self.svd_type == "full-rank":
@@ -226,6 +235,9 @@ class ProjectorCalculator:
             else:
                 p1 = ops.matmul(pend["Q1"], ops.matmul(pend["Q2"], Us, transpose_a=True), transpose_a=True)
                 p2 = ops.matmul(pend["Q4"], ops.matmul(pend["Q3"], Vs))
+        if stream is not None:
+            pend["ready"] = torch.cuda.Event()
+            pend["ready"].record(stream)       # the projector pair is complete on the side stream
         return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
 
     def calculate_half_system(self, ipeps, sites, k):
@@ -249,6 +261,13 @@ class DirectionalMover:
         self.calculate_projectors = self.projector_calculator.calculate
         self.n_streams = int(os.environ.get("ACETN_B200_STREAMS", "4")) if n_streams is None else n_streams
         self._streams = None
+        self._bulk_stream = None
+        # staggered phases (half-system rSVD): the throughput-bound stages of all tasks (quarter tensors + encodings, then the
+        # absorptions of each move as soon as its projectors exist) are queued in task order on ONE low-priority "bulk" stream;
+        # each task's rSVD chain runs on its own HIGH-priority stream.  The block scheduler then serves the ~500 small
+        # latency-bound launches of a chain (TSQR, Jacobi, CRT) ahead of the pending CTAs of the next task's DGEMMs instead
+        # of queueing them behind whole 4 ms kernels, and the tasks no longer go through their latency-bound stages in lockstep.
+        self.stagger = os.environ.get("ACETN_B200_STAGGER", "1") != "0"
 
     def _side_streams(self, device):
         if self.n_streams <= 1:
@@ -317,14 +336,51 @@ class DirectionalMover:
         read and write disjoint boundary tensors, which is what the reference's distributed schedule relies on
         (directional_mover.py:183-271); the Omega draws keep the sequential order (first move's sites, then the
         second's)."""
-        tasks = []
-        for k, line in moves:
-            tasks += self.move_tasks(ipeps, k, line)
-        p1, p2 = self._projectors_of_tasks(ipeps, tasks)
-        for t in tasks:
-            k = t["k"]
-            self.renormalize_boundary(ipeps, {t["i"]: p1[(k, t["i"])], t["j"]: p1[(k, t["j"])]},
-                                      {t["i"]: p2[(k, t["i"])], t["j"]: p2[(k, t["j"])]}, t["s1"], t["s2"], t["i"], t["j"], k)
+        groups = [self.move_tasks(ipeps, k, line) for k, line in moves]
+        tasks = [t for g in groups for t in g]
+        if not (self.stagger and self.n_streams > 1 and len(groups) > 1 and self.projector_calculator.projectors == "half-system"
+                and self.projector_calculator.svd_type == "rsvd"):
+            p1, p2 = self._projectors_of_tasks(ipeps, tasks)
+            for t in tasks:
+                self._absorb_task(ipeps, t, p1, p2)
+            return
+        # staggered schedule: the moves of the phase touch disjoint boundary tensors (see above), so the absorptions of a move
+        # may run -- on their own stream -- while the projectors of the following moves are still being computed
+        pc = self.projector_calculator
+        device = ipeps[tasks[0]["s1"]]['A'].device
+        if device.type != "cuda":
+            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        if self._bulk_stream is None:
+            self._bulk_stream = torch.cuda.Stream(device=device, priority=0)
+            self._hi_streams = []
+        while len(self._hi_streams) < min(len(tasks), 16):       # one chain per stream: finish() synchronises whole streams
+            self._hi_streams.append(torch.cuda.Stream(device=device, priority=-1))
+        bulk, streams = self._bulk_stream, self._hi_streams[:min(len(tasks), 16)]
+        omegas = [pc.draw_omega(ipeps, t["plaq"], t["k"]) for t in tasks]      # reference order of the RNG draws
+        main = torch.cuda.current_stream(device)
+        for st in streams + [bulk]:
+            st.wait_stream(main)
+        pend = [pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n], bulk=bulk)
+                for n, t in enumerate(tasks)]
+        p1, p2 = {}, {}
+        n0 = 0
+        for g in groups:
+            for t, pd in zip(g, pend[n0:n0 + len(g)]):
+                p1[(t["k"], t["key"])], p2[(t["k"], t["key"])] = pc.finish(pd)
+                if pd.get("ready") is not None:
+                    bulk.wait_event(pd["ready"])
+            n0 += len(g)
+            with torch.cuda.stream(bulk):          # outputs and scratch come from this stream's pool
+                for t in g:
+                    self._absorb_task(ipeps, t, p1, p2)
+        for st in streams + [bulk]:
+            main.wait_stream(st)
+        del pend
+
+    def _absorb_task(self, ipeps, t, p1, p2):
+        k = t["k"]
+        self.renormalize_boundary(ipeps, {t["i"]: p1[(k, t["i"])], t["j"]: p1[(k, t["j"])]},
+                                  {t["i"]: p2[(k, t["i"])], t["j"]: p2[(k, t["j"])]}, t["s1"], t["s2"], t["i"], t["j"], k)
 
     def left_right_move(self, ipeps, x1, x2):
         """Single-process counterpart of left_right_move_dist (directional_mover.py:183-226)."""

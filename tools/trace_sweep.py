@@ -39,6 +39,10 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     ctmrg(ip, cfg, mover)
     torch.cuda.synchronize()
 
+chrome = os.path.splitext(args.out)[0] + "_chrome.json"
+os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+prof.export_chrome_trace(chrome)
+os.system(f"gzip -f {chrome}")
 ev = []
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None:
