@@ -54,8 +54,21 @@ class B200Compute:
         if not tasks:
             return []
         device = ipeps[tasks[0]["s1"]]['A'].device
-        streams = self.mover._side_streams(device)
         main = torch.cuda.current_stream(device)
+        if group_size <= 1 and len(tasks) > 1 and self.mover.staggered():
+            # several tasks on this rank: quarter tensors + encodings in task order on the low-priority bulk stream, every rSVD
+            # chain on its own high-priority stream (renormalization.DirectionalMover.move_pair)
+            bulk, streams = self.mover.phase_streams(device, len(tasks))
+            for st in streams + [bulk]:
+                st.wait_stream(main)
+            pend = [self.pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n], bulk=bulk)
+                    for n, t in enumerate(tasks)]
+            out = [self.pc.finish(pd) for pd in pend]
+            for st in streams + [bulk]:
+                main.wait_stream(st)
+            del pend
+            return [(a.contiguous(), b.contiguous()) for a, b in out]
+        streams = self.mover._side_streams(device)
         for st in streams:
             if st is not None:
                 st.wait_stream(main)

@@ -276,6 +276,22 @@ class DirectionalMover:
             self._streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
         return self._streams
 
+    def staggered(self):
+        """True when the phase schedule with one bulk stream + one high-priority stream per rSVD chain applies."""
+        pc = self.projector_calculator
+        return self.stagger and self.n_streams > 1 and pc.projectors == "half-system" and pc.svd_type == "rsvd"
+
+    def phase_streams(self, device, ntasks):
+        """(bulk, [chain streams]): the low-priority stream of the throughput-bound stages and one high-priority stream per
+        task (at most 16; finish() synchronises a whole stream, so chains do not share one unless there are more tasks)."""
+        if self._bulk_stream is None:
+            self._bulk_stream = torch.cuda.Stream(device=device, priority=0)
+            self._hi_streams = []
+        n = max(1, min(ntasks, 16))
+        while len(self._hi_streams) < n:
+            self._hi_streams.append(torch.cuda.Stream(device=device, priority=-1))
+        return self._bulk_stream, self._hi_streams[:n]
+
     def _projectors_of_line(self, ipeps, plaquettes, k):
         """All projector pairs of one move: {key: (proj1, proj2)} ; plaquettes = [(key, sites)]."""
         pc = self.projector_calculator
@@ -338,8 +354,7 @@ class DirectionalMover:
         second's)."""
         groups = [self.move_tasks(ipeps, k, line) for k, line in moves]
         tasks = [t for g in groups for t in g]
-        if not (self.stagger and self.n_streams > 1 and len(groups) > 1 and self.projector_calculator.projectors == "half-system"
-                and self.projector_calculator.svd_type == "rsvd"):
+        if not (self.staggered() and len(groups) > 1):
             p1, p2 = self._projectors_of_tasks(ipeps, tasks)
             for t in tasks:
                 self._absorb_task(ipeps, t, p1, p2)
@@ -350,12 +365,7 @@ class DirectionalMover:
         device = ipeps[tasks[0]["s1"]]['A'].device
         if device.type != "cuda":
             raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
-        if self._bulk_stream is None:
-            self._bulk_stream = torch.cuda.Stream(device=device, priority=0)
-            self._hi_streams = []
-        while len(self._hi_streams) < min(len(tasks), 16):       # one chain per stream: finish() synchronises whole streams
-            self._hi_streams.append(torch.cuda.Stream(device=device, priority=-1))
-        bulk, streams = self._bulk_stream, self._hi_streams[:min(len(tasks), 16)]
+        bulk, streams = self.phase_streams(device, len(tasks))
         omegas = [pc.draw_omega(ipeps, t["plaq"], t["k"]) for t in tasks]      # reference order of the RNG draws
         main = torch.cuda.current_stream(device)
         for st in streams + [bulk]:

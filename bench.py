@@ -176,7 +176,13 @@ def run_b200(args):
         raise RuntimeError("bench.py: no CUDA device; the b200 backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
+        # exactly ONE line on stdout: native libraries (NCCL's version banner, NCCL_DEBUG output) write to fd 1 directly, so fd 1
+        # is pointed at stderr for the duration of the run and the JSON line goes to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     n = max(world, 1)
     gsz = 1
@@ -243,14 +249,28 @@ def run_b200(args):
                 "E": [e.cpu().pin_memory() for e in ip[s]['E']]} for s in ip.site_list}
     h2d = sum(h["A"].numel() + sum(c.numel() for c in h["C"]) + sum(e.numel() for e in h["E"]) for h in host.values()) * 8
     d2h = sum(sum(c.numel() for c in h["C"]) + sum(e.numel() for e in h["E"]) for h in host.values()) * 8
+    # N > 1: the state is replicated on every rank (like the reference's distributed mode), but it crosses PCIe only once:
+    # site s is uploaded / downloaded by rank (index of s) % world, and replicated to the other ranks over NVLink (NCCL
+    # broadcast).  h2d / d2h count the bytes of the whole job per step.
+    site_owner = {s: i % world for i, s in enumerate(ip.site_list)}
 
     def e2e_step():
         for s in ip.site_list:
             h = host[s]
-            ip[s] = SiteTensor(h["A"].to(dev, non_blocking=True), [c.to(dev, non_blocking=True) for c in h["C"]],
-                               [e.to(dev, non_blocking=True) for e in h["E"]])
+            if site_owner[s] == rank:
+                st = SiteTensor(h["A"].to(dev, non_blocking=True), [c.to(dev, non_blocking=True) for c in h["C"]],
+                                [e.to(dev, non_blocking=True) for e in h["E"]])
+            else:
+                mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)     # noqa: E731
+                st = SiteTensor(mk(h["A"]), [mk(c) for c in h["C"]], [mk(e) for e in h["E"]])
+            if world > 1:
+                for t in [st['A']] + list(st['C']) + list(st['E']):
+                    dist.broadcast(t, src=site_owner[s])
+            ip[s] = st
         sweep()
         for s in ip.site_list:
+            if site_owner[s] != rank:
+                continue
             for k in range(4):
                 host[s]["C"][k].copy_(ip[s]['C'][k], non_blocking=True)
                 host[s]["E"][k].copy_(ip[s]['E'][k], non_blocking=True)
@@ -383,7 +403,11 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
