@@ -48,9 +48,14 @@ __device__ __forceinline__ double rotate_pair(double* xa, double* xb, double* ja
     // relative criterion |xa.xb| <= tol |xa||xb| tested without sqrt/div; the ratio is only formed for pairs that rotate
     const double r2 = sab * sab, den = saa * sbb;
     if (r2 <= tol * tol * den) return 0.0;
-    const double rel = sqrt(r2 / den);
-    double zeta = (sbb - saa) / (2.0 * sab);
-    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (sbb - saa) / (2 sab), written with one sqrt and one division (this
+    // scalar chain is the critical path of a local step); the return value only says "rotated" (1.0): a sweep without any
+    // rotation is the convergence criterion
+    const double d = sbb - saa;
+    const double h = sqrt(d * d + 4.0 * r2);
+    double t = (2.0 * sab) / (fabs(d) + h);
+    t = d >= 0.0 ? t : -t;
+    const double rel = 1.0;
     double cs = rsqrt(1.0 + t * t), sn = cs * t;
     double2* ja2 = reinterpret_cast<double2*>(ja);
     double2* jb2 = reinterpret_cast<double2*>(jb);

@@ -21,15 +21,21 @@ constexpr int TS_NW = TS_CH / 32;
 // partial sum through shared memory and 32 FMAs for the update -- no warp shuffles on the critical path.
 
 // Factor one chunk: P[r0:r0+rows, 0:b] = H_0 ... H_{b-1} [R; 0].  Reflectors overwrite the strictly lower part of P.
+//
+// Step j works on the RAW pivot column (as it stands after the previous updates), which its owner lanes (lane j of every warp)
+// dumped to shared memory at the end of step j-1 together with their partial sums of squares:
+//   v = [0 .. 0, 1, x_{j+1..} / (alpha - beta)],  H_j = I - tau v v^T   (LAPACK dlarfg)
+//   x_c <- x_c - vraw (g * vraw^T x_c),  vraw = (alpha - beta) v,  g = tau / (alpha - beta)^2 = 1 / (nrm (nrm + |alpha|))
+// so nobody has to scale the pivot column inside the loop (the 1/(alpha - beta) factors and the diagonal beta are applied when
+// the reflectors are written out), every warp executes the same ~200 instructions per step, and a step needs two barriers.
 __global__ void __launch_bounds__(TS_CH, 1)
 tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
                    double* __restrict__ tau_out, const int* __restrict__ run_flag) {
     if (run_flag != nullptr && *run_flag == 0) return;    // second BCGS pass found the panel already orthogonal to eps
-    __shared__ __align__(16) double v_s[TS_CH];   // current reflector (0 above its diagonal, 1 on it)
-    __shared__ double part[TS_NW][TS_PB];    // per-warp partial dots
-    __shared__ double partn[TS_NW];          // per-warp partial norms of the pivot column
-    __shared__ double alpha_s;
-    __shared__ double tau_s[TS_PB];
+    __shared__ __align__(16) double col_s[TS_CH];   // raw pivot column of the current step
+    __shared__ double part[TS_NW][TS_PB];           // per-warp partial dots
+    __shared__ double partn[TS_NW];                 // per-warp partial sums of squares of the pivot column below the diagonal
+    __shared__ double tau_s[TS_PB], beta_s[TS_PB], scale_s[TS_PB];
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
@@ -42,9 +48,9 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
         int r = rbase + i;
         x[i] = (r < rows && c < b) ? P[(r0 + r) * ld + c] : 0.0;
     }
-    if (tid < TS_PB) tau_s[tid] = 0.0;
+    if (tid < TS_PB) { tau_s[tid] = 0.0; beta_s[tid] = 0.0; scale_s[tid] = 1.0; }
 
-    // sum of 32 products with 8 independent chains (the FP64 pipe has a long dependent latency)
+    // sum of 32 products with 8 independent chains
 #define TS_DOT32(res, EXPR)                                                     \
     {                                                                           \
         double _p[8];                                                           \
@@ -53,88 +59,82 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
             _Pragma("unroll") for (int _k = 0; _k < 8; _k++) { int i = _q * 8 + _k; _p[_k] += (EXPR); } \
         res = ((_p[0] + _p[1]) + (_p[2] + _p[3])) + ((_p[4] + _p[5]) + (_p[6] + _p[7])); \
     }
-
-    // norm data of column 0 (later columns get theirs at the end of the previous step)
-    if (c == 0) {
-        double pn;
-        if (rbase > 0) { TS_DOT32(pn, x[i] * x[i]); } else { TS_DOT32(pn, (i > 0) ? x[i] * x[i] : 0.0); }
-        partn[w] = pn;
-        if (w == 0) alpha_s = x[0];
+    // owner lanes of column jj: dump the raw column and the partial sum of squares of its rows below the diagonal
+#define TS_PUBLISH(jj)                                                          \
+    {                                                                           \
+        double2* _d = reinterpret_cast<double2*>(col_s + rbase);                \
+        _Pragma("unroll") for (int _i = 0; _i < 16; _i++) _d[_i] = make_double2(x[2 * _i], x[2 * _i + 1]); \
+        double pn;                                                              \
+        if (rbase > (jj)) { TS_DOT32(pn, x[i] * x[i]); }                        \
+        else if (rbase + 31 <= (jj)) pn = 0.0;                                  \
+        else { TS_DOT32(pn, (rbase + i > (jj)) ? x[i] * x[i] : 0.0); }          \
+        partn[w] = pn;                                                          \
     }
+
+    if (c == 0) TS_PUBLISH(0);
     __syncthreads();
     for (int j = 0; j < nref; j++) {
-        // ---- reflector j from column j, rows >= j   (partn / alpha_s were produced by the previous step)
-        double ss = 0.0;
-#pragma unroll
-        for (int k = 0; k < TS_NW; k++) ss += partn[k];
-        const double alpha = alpha_s;
-        double tau = 0.0, beta = alpha, scale = 0.0;
+        // ---- reflector j (every thread computes the same scalars)
+        double ss = ((partn[0] + partn[1]) + (partn[2] + partn[3])) + ((partn[4] + partn[5]) + (partn[6] + partn[7]));
+        const double alpha = col_s[j];
+        double g = 0.0, amb = 0.0;                 // g = tau / (alpha - beta)^2,  amb = alpha - beta
         if (ss != 0.0) {
-            double nrm = sqrt(alpha * alpha + ss);
-            beta = alpha >= 0.0 ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        if (c == j) {
-            if (rbase > j) {                     // whole slice below the pivot (warp-uniform)
-#pragma unroll
-                for (int i = 0; i < 32; i++) { x[i] *= scale; v_s[rbase + i] = x[i]; }
-            } else if (rbase + 31 < j) {         // whole slice above the pivot
-#pragma unroll
-                for (int i = 0; i < 32; i++) v_s[rbase + i] = 0.0;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    int r = rbase + i;
-                    if (r > j) { x[i] *= scale; v_s[r] = x[i]; }
-                    else if (r == j) { x[i] = beta; v_s[r] = 1.0; }
-                    else v_s[r] = 0.0;
-                }
-            }
-            if (w == 0) tau_s[j] = tau;
-        }
-        __syncthreads();
-        // ---- apply H_j to the trailing columns
+            const double nrm = sqrt(alpha * alpha + ss);
+            const double beta = alpha >= 0.0 ? -nrm : nrm;
+            amb = alpha - beta;
+            g = 1.0 / (nrm * (nrm + fabs(alpha)));
+            // tau = (beta - alpha) / beta = g amb^2 and 1 / amb = -g beta: no further divisions (they would make warp 0 late at the barrier)
+            if (tid == 0) { tau_s[j] = g * amb * amb; beta_s[j] = beta; scale_s[j] = -g * beta; }
+        } else if (tid == 0) { tau_s[j] = 0.0; beta_s[j] = alpha; scale_s[j] = 0.0; }
+        // ---- vraw . x_c over this warp's 32 rows (rows above the pivot do not take part; the pivot row carries alpha - beta)
+        // (j < b <= 32: the pivot row always lies in warp 0, every other warp is entirely below it)
         double vv[32];
+        double dsum;
         {
-            const double2* v2 = reinterpret_cast<const double2*>(v_s + rbase);
+            const double2* v2 = reinterpret_cast<const double2*>(col_s + rbase);
 #pragma unroll
             for (int i = 0; i < 16; i++) { double2 t = v2[i]; vv[2 * i] = t.x; vv[2 * i + 1] = t.y; }
+            if (w == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) vv[i] = i > j ? vv[i] : (i == j ? amb : 0.0);
+            }
+            TS_DOT32(dsum, vv[i] * x[i]);
         }
-        double dsum;
-        TS_DOT32(dsum, vv[i] * x[i]);
         part[w][c] = dsum;
         __syncthreads();
-        if (c > j && c < b) {
-            double wc = 0.0;
+        {
+            double wc = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + ((part[4][c] + part[5][c]) + (part[6][c] + part[7][c]));
+            wc = (c > j && c < b) ? wc * g : 0.0;      // finished columns (c <= j) are left alone
+            // the owner lanes of column j+1 publish it for the next step while the update is still being issued
+            const bool pub = (c == j + 1) && (j + 1 < nref);
+            double2* dst = reinterpret_cast<double2*>(col_s + rbase);
 #pragma unroll
-            for (int k = 0; k < TS_NW; k++) wc += part[k][c];
-            wc *= tau;
-#pragma unroll
-            for (int i = 0; i < 32; i++) x[i] -= vv[i] * wc;
-            if (c == j + 1) {   // norm data of the next pivot column
+            for (int i = 0; i < 16; i++) {
+                x[2 * i] -= vv[2 * i] * wc;
+                x[2 * i + 1] -= vv[2 * i + 1] * wc;
+                if (pub) dst[i] = make_double2(x[2 * i], x[2 * i + 1]);
+            }
+            if (pub) {
                 double pn;
-                if (rbase > j + 1) { TS_DOT32(pn, x[i] * x[i]); }
-                else if (rbase + 31 <= j + 1) {
-                    pn = 0.0;
-                    if (rbase + 31 == j + 1) alpha_s = x[31];
-                } else {
-                    TS_DOT32(pn, (rbase + i > j + 1) ? x[i] * x[i] : 0.0);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) if (rbase + i == j + 1) alpha_s = x[i];
-                }
+                if (w > 0) { TS_DOT32(pn, x[i] * x[i]); }
+                else { TS_DOT32(pn, (i > j + 1) ? x[i] * x[i] : 0.0); }
                 partn[w] = pn;
             }
         }
         __syncthreads();
     }
-    __syncthreads();
-    // reflectors (and R) back to P; R block (b x b, zero below the diagonal / beyond rows) to the stack
+    // reflectors (scaled to unit diagonal) and R back to P; R block (b x b, zero below the diagonal / beyond rows) to the stack
+    {
+        const double sc = c < TS_PB ? scale_s[c] : 1.0, be = beta_s[c];
+        const bool has_ref = c < nref;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        int r = rbase + i;
-        if (r < rows && c < b) P[(r0 + r) * ld + c] = x[i];
-        if (r < b && c < b) Rstack[((int64_t)blockIdx.x * b + r) * b + c] = (r <= c && r < nref) ? x[i] : 0.0;
+        for (int i = 0; i < 32; i++) {
+            int r = rbase + i;
+            double v = x[i];
+            if (has_ref) v = r > c ? v * sc : (r == c ? be : v);
+            if (r < rows && c < b) P[(r0 + r) * ld + c] = v;
+            if (r < b && c < b) Rstack[((int64_t)blockIdx.x * b + r) * b + c] = (r <= c && r < nref) ? v : 0.0;
+        }
     }
     if (tid < b) tau_out[(int64_t)blockIdx.x * b + tid] = tau_s[tid];
 }
