@@ -1,9 +1,12 @@
-"""B200 counterparts of the full-update pieces on the hot path: build_norm_tensor
-(acetn/evolution/full_update.py:163-227) and the ALS inner solver (acetn/evolution/als_solver.py).
+"""B200 counterparts of the full-update pieces: build_norm_tensor (acetn/evolution/full_update.py:163-227), the ALS inner
+solver (acetn/evolution/als_solver.py) and -- SURVEY.md 8f-1 -- the callers around them in one bond update: QR split
+(tensor_update.py:53-75), positive_approx / gauge_fix (full_update.py:262-343), finalize_reduced_tensors (:121-161).
 
-The callers around them (QR split, positive_approx, gauge_fix, finalize, gates -- SURVEY.md 8f-1) stay in the
-reference; `ALSSolver` keeps the reference's constructor/solve() shape so it can replace
-`ALSSolver(n12, a12g, ar_shape, config).solve()` when `config.backend == "b200"` (als_solver.py:48-51)."""
+Everything dense runs on the library's own kernels (no cuSOLVER): contractions = gather + batched K1 DGEMM (`ops.contract`),
+thin QR = K4 Householder TSQR + one K1 product for R, symmetric eigen-decomposition / SVD / pseudo-inverse of the small
+matrices (<= 256 x 256) = K5 one-sided Jacobi, ALS loop = K6.  `ALSSolver` keeps the reference's constructor/solve() shape so
+it can replace `ALSSolver(n12, a12g, ar_shape, config).solve()` when `config.backend == "b200"` (als_solver.py:48-51);
+`full_update_bond` is `FullUpdater.tensor_update` (full_update.py:34-63)."""
 import torch
 
 from . import ops
@@ -49,11 +52,11 @@ class ALSSolver:
             raise NotImplementedError("backend='b200': als_method must be 'cholesky'")
 
     def initialize_tensors(self):
-        """als_solver.py:112-146 (a 2nD x 2nD SVD: host-side small dense LA)."""
+        """als_solver.py:112-146 (SVD of the (nD pD) x (nD pD) gate-tensor product on K5)."""
         nD, bD, pD = self.ar_shape
         m = self.a12g.permute(0, 2, 1, 3).reshape(nD * pD, nD * pD)
-        U, S, Vh = torch.linalg.svd(m)
-        V = Vh.mH
+        U, S, Vh = svd_small(m)
+        V = Vh.t()
         S = torch.sqrt(S[:bD] / S[0])
         a1r = (U[:, :bD].reshape(nD, pD, bD) * S).permute(0, 2, 1).contiguous()
         a2r = (V[:, :bD].reshape(nD, pD, bD) * S).permute(0, 2, 1).contiguous()
@@ -64,3 +67,117 @@ class ALSSolver:
         a1r, a2r, n12g = self.initialize_tensors()
         a1r, a2r, self.info = ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon)
         return a1r, a2r
+
+
+# ---- small dense linear algebra on the library's kernels ------------------------------------------------------------
+def svd_small(M):
+    """torch.linalg.svd(M) of a small square matrix: M = U diag(S) Vh, S descending (K5: M = Jt^T diag(S) Wt)."""
+    S, Wt, Jt, _ = ops.jacobi_svd(M.contiguous())
+    return Jt.t().contiguous(), S, Wt
+
+
+def eigh_sym(N):
+    """Eigen-decomposition of a symmetric matrix, N = V diag(w) V^T (torch.linalg.eigh up to the order of the pairs): the left
+    singular vectors of K5 are orthonormal eigenvectors, the eigenvalues are their Rayleigh quotients (signed)."""
+    N = N.contiguous()
+    _, _, Jt, _ = ops.jacobi_svd(N)
+    w = (ops.matmul(Jt, N) * Jt).sum(dim=1)
+    return w, Jt.t().contiguous()
+
+
+def pinv_small(R, atol=1e-12):
+    """torch.linalg.pinv(R, atol=atol) (singular values <= atol are dropped; rtol = 0 as in torch when atol is given)."""
+    S, Wt, Jt, _ = ops.jacobi_svd(R.contiguous())
+    inv = torch.where(S > atol, 1.0 / S, torch.zeros_like(S))
+    return ops.matmul((Wt * inv[:, None]).contiguous(), Jt, transpose_a=True)
+
+
+def qr_small(M):
+    """torch.linalg.qr(M) of a tall matrix up to the signs of the columns of Q / rows of R: Q = K4 (Householder TSQR), R = Q^T M."""
+    M = M.contiguous()
+    Q = ops.orthonormalize(M.clone())
+    return Q, ops.matmul(Q, M, transpose_a=True)
+
+
+# ---- the callers around the norm tensor / ALS (SURVEY.md 8f-1) --------------------------------------------------------
+def decompose_site_tensors(a1, a2):
+    """tensor_update.py:53-68."""
+    bD, pD = a1.shape[3:]
+    nD = min(bD ** 3, pD * bD)
+    a1q, a1r = qr_small(a1.permute(2, 3, 1, 0, 4).reshape(bD ** 3, pD * bD))        # "lurdp->rdulp"
+    a2q, a2r = qr_small(a2.permute(3, 0, 1, 2, 4).reshape(bD ** 3, pD * bD))        # "lurdp->dlurp"
+    return a1q.reshape(bD, bD, bD, nD), a1r.reshape(nD, bD, pD), a2q.reshape(bD, bD, bD, nD), a2r.reshape(nD, bD, pD)
+
+
+def recompose_site_tensors(a1q, a1r, a2q, a2r):
+    """tensor_update.py:70-75."""
+    return contract("rdux,xlp->lurdp", a1q, a1r).contiguous(), contract("dlux,xrp->lurdp", a2q, a2r).contiguous()
+
+
+def positive_approx(n12, cutoff=1e-12):
+    """full_update.py:262-293."""
+    nD = n12.shape[0]
+    N = n12.reshape(nD ** 2, nD ** 2).clone()
+    # torch.linalg.eigh (UPLO='L') reads the lower triangle only; on a not-yet-converged environment the norm tensor is visibly
+    # non-symmetric, so the matrix the reference actually decomposes is tril(N) mirrored
+    N = torch.tril(N) + torch.tril(N, -1).t()
+    nw, nz = eigh_sym(N)
+    lo = float(nw.min())
+    while lo < cutoff:
+        N += 2 * max(cutoff, abs(lo)) * torch.eye(nD ** 2, dtype=N.dtype, device=N.device)
+        nw, nz = eigh_sym(N)
+        lo = float(nw.min())
+    return nz.reshape(nD, nD, nD ** 2) * torch.sqrt(nw)
+
+
+def gauge_fix(nz, a12g, atol=1e-12):
+    """full_update.py:296-343."""
+    nD = a12g.shape[0]
+    _, nzyr = qr_small(nz.permute(2, 1, 0).reshape(nD ** 3, nD))        # "yxz->zxy"
+    _, nzxr = qr_small(nz.permute(2, 0, 1).reshape(nD ** 3, nD))        # "yxz->zyx"
+    nzyr_inv = pinv_small(nzyr, atol=atol)
+    nzxr_inv = pinv_small(nzxr, atol=atol)
+    nz = contract("yxz,xw->yzw", nz, nzxr_inv)
+    nz = contract("yzw,yv->zvw", nz, nzyr_inv).contiguous()
+    n12 = contract("zvw,zVW->vwVW", nz, nz).contiguous()
+    a12g = contract("zx,yxpq->yzpq", nzxr, a12g)
+    a12g = contract("wy,yzpq->wzpq", nzyr, a12g).contiguous()
+    return n12, a12g, nzxr_inv, nzyr_inv
+
+
+def finalize_reduced_tensors(a1r, a2r, nzxr_inv=None, nzyr_inv=None):
+    """full_update.py:121-161."""
+    if nzyr_inv is not None:
+        a1r = contract("yz,zup->yup", nzyr_inv, a1r)
+        a2r = contract("xw,wvq->xvq", nzxr_inv, a2r)
+    nD, bD, pD = a1r.shape
+    q1, r1 = qr_small(a1r.permute(0, 2, 1).reshape(nD * pD, bD))
+    q2, r2 = qr_small(a2r.permute(0, 2, 1).reshape(nD * pD, bD))
+    U, s, Vh = svd_small(ops.matmul(r1, r2.t().contiguous()))
+    s = torch.sqrt(s[:bD] / s.norm())
+    r1 = (U[:, :bD] * s).contiguous()                       # "ab,b->ab"
+    r2 = (Vh[:bD, :] * s[:, None]).contiguous()             # "ba,b->ba"
+    a1r = contract("ypa,au->yup", q1.reshape(nD, pD, bD), r1).contiguous()
+    a2r = contract("xqb,vb->xvq", q2.reshape(nD, pD, bD), r2).contiguous()
+    return a1r, a2r
+
+
+def full_update_bond(ipeps, bond, a1, a2, gate, config):
+    """FullUpdater.tensor_update (full_update.py:34-96): a1, a2 in the bond frame, gate (d,d,d,d) -> updated, normalised a1, a2."""
+    a1q, a1r, a2q, a2r = decompose_site_tensors(a1, a2)
+    n12 = build_norm_tensor(ipeps, bond, a1q, a2q)
+    a12g = contract("yup,xuq->yxpq", a1r, a2r)
+    a12g = contract("yxpq,pqrs->yxrs", a12g, gate.contiguous()).contiguous()
+    nz = positive_approx(n12, cutoff=config.positive_approx_cutoff)
+    inv = (None, None)
+    if config.use_gauge_fix:
+        n12, a12g, nzxr_inv, nzyr_inv = gauge_fix(nz, a12g, atol=config.gauge_fix_atol)
+        inv = (nzxr_inv, nzyr_inv)
+    else:
+        n12 = contract("xyz,XYz->xyXY", nz.contiguous(), nz.contiguous()).contiguous()
+    b1, b2 = ALSSolver(n12, a12g, tuple(a1r.shape), config).solve()
+    b1, b2 = finalize_reduced_tensors(b1, b2, *inv)
+    a1n, a2n = recompose_site_tensors(a1q, b1, a2q, b2)
+    ops.frob_normalize(a1n)
+    ops.frob_normalize(a2n)
+    return a1n, a2n

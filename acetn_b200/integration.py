@@ -11,6 +11,8 @@
     ipeps_config.py:103-109 -- the north star forbids that here);
   * `acetn.ipeps.ipeps.ctmrg` (the name `Ipeps.renormalize` calls, ipeps.py:93-97) is wrapped: backend "b200" routes to
     acetn_b200.renormalization.ctmrg, anything else to the untouched reference function (which stays the oracle path);
+  * `acetn.evolution.full_update.FullUpdater.tensor_update` (one bond update: QR split, norm tensor, positive_approx,
+    gauge_fix, ALS, finalisation) routes to `acetn_b200.evolution.full_update_bond` for backend "b200";
   * `acetn.renormalization.projectors.{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}` are NOT replaced
     globally: backend "torch" keeps the reference numerics bit for bit.
 The reference's SiteTensor / TensorNetwork objects are used as they are: the B200 mover only needs `ipeps[site]['A'|'C'|'E']`,
@@ -100,5 +102,15 @@ def install(acetn_module=None):
         return ref_solve(self)
 
     als_mod.ALSSolver.solve = solve
+
+    # ---- the callers around them: one whole bond update on the library's kernels ---------------------------
+    ref_tensor_update = fu_mod.FullUpdater.tensor_update
+
+    def tensor_update(self, a1, a2, bond):
+        if self.backend == "b200":
+            return b200_evo.full_update_bond(self.ipeps, bond, a1.contiguous(), a2.contiguous(), self.gate[bond], self.config)
+        return ref_tensor_update(self, a1, a2, bond)
+
+    fu_mod.FullUpdater.tensor_update = tensor_update
     ipeps_mod._acetn_b200_installed = True
     return acetn_module

@@ -603,3 +603,94 @@ def als_initial_guess(a12g, ar_shape):
     a1r = torch.einsum("ypu,u->yup", U[:, :bD].reshape(nD, pD, bD), S)
     a2r = torch.einsum("xqv,v->xvq", V[:, :bD].reshape(nD, pD, bD), S)
     return a1r, a2r
+
+
+# --------------------------------------------------------------------------------------
+# the callers around the norm tensor / ALS in one full-update bond update:
+# QR split, positive approximation, gauge fix, finalisation, recomposition
+# (acetn/evolution/tensor_update.py:53-75, full_update.py:34-161, 262-343)
+# --------------------------------------------------------------------------------------
+def decompose_site_tensors(a1, a2):
+    """tensor_update.py:53-68 : a = (environment part q)(bond-local part r); a1, a2 already in the bond frame."""
+    bD, pD = a1.shape[3:]
+    nD = min(bD ** 3, pD * bD)
+    a1q, a1r = torch.linalg.qr(torch.einsum("lurdp->rdulp", a1).reshape(bD ** 3, pD * bD))
+    a2q, a2r = torch.linalg.qr(torch.einsum("lurdp->dlurp", a2).reshape(bD ** 3, pD * bD))
+    return a1q.reshape(bD, bD, bD, nD), a1r.reshape(nD, bD, pD), a2q.reshape(bD, bD, bD, nD), a2r.reshape(nD, bD, pD)
+
+
+def recompose_site_tensors(a1q, a1r, a2q, a2r):
+    """tensor_update.py:70-75."""
+    return torch.einsum("rdux,xlp->lurdp", a1q, a1r), torch.einsum("dlux,xrp->lurdp", a2q, a2r)
+
+
+def positive_approx(n12, cutoff=1e-12):
+    """full_update.py:262-293 : nz with N ~ nz nz^T, the spectrum shifted until its smallest eigenvalue is >= cutoff."""
+    nD = n12.shape[0]
+    N = n12.reshape(nD ** 2, nD ** 2).clone()
+    nw, nz = torch.linalg.eigh(N)
+    while nw[0] < cutoff:
+        N += 2 * max(cutoff, abs(float(nw[0]))) * torch.eye(nD ** 2, dtype=N.dtype)
+        nw, nz = torch.linalg.eigh(N)
+    return nz.reshape(nD, nD, nD ** 2) * torch.sqrt(nw)
+
+
+def gauge_fix(nz, a12g, atol=1e-12):
+    """full_update.py:296-343."""
+    nD = a12g.shape[0]
+    _, nzyr = torch.linalg.qr(torch.einsum("yxz->zxy", nz).reshape(nD ** 3, nD))
+    _, nzxr = torch.linalg.qr(torch.einsum("yxz->zyx", nz).reshape(nD ** 3, nD))
+    nzyr_inv = torch.linalg.pinv(nzyr, atol=atol)
+    nzxr_inv = torch.linalg.pinv(nzxr, atol=atol)
+    nz = torch.einsum("yxz,xw->yzw", nz, nzxr_inv)
+    nz = torch.einsum("yzw,yv->zvw", nz, nzyr_inv)
+    n12 = torch.einsum("zvw,zVW->vwVW", nz, nz.conj())
+    a12g = torch.einsum("zx,yxpq->yzpq", nzxr, a12g)
+    a12g = torch.einsum("wy,yzpq->wzpq", nzyr, a12g)
+    return n12, a12g, nzxr_inv, nzyr_inv
+
+
+def finalize_reduced_tensors(a1r, a2r, nzxr_inv=None, nzyr_inv=None):
+    """full_update.py:121-161 (Fig. 12(b) of arXiv:1405.3259): undo the gauge fix, balance the bond."""
+    if nzyr_inv is not None:
+        a1r = torch.einsum("yz,zup->yup", nzyr_inv, a1r)
+        a2r = torch.einsum("xw,wvq->xvq", nzxr_inv, a2r)
+    nD, bD, pD = a1r.shape
+    q1, r1 = torch.linalg.qr(torch.einsum("yup->ypu", a1r).reshape(nD * pD, bD))
+    q2, r2 = torch.linalg.qr(torch.einsum("xvq->xqv", a2r).reshape(nD * pD, bD))
+    U, s, Vh = torch.linalg.svd(torch.einsum("au,bu->ab", r1, r2))
+    s = torch.sqrt(s[:bD] / s.norm())
+    r1 = torch.einsum("ab,b->ab", U[:, :bD], s)
+    r2 = torch.einsum("ba,b->ba", Vh[:bD, :], s)
+    a1r = torch.einsum("ypa,au->yup", q1.reshape(nD, pD, bD), r1)
+    a2r = torch.einsum("xqb,vb->xvq", q2.reshape(nD, pD, bD), r2)
+    return a1r, a2r
+
+
+def full_update_bond(cell: Cell, bond, a1, a2, gate, use_gauge_fix=True, gauge_fix_atol=1e-12, positive_approx_cutoff=1e-12,
+                     als_niter=100, als_tol=1e-15, als_epsilon=1e-12):
+    """FullUpdater.tensor_update (full_update.py:34-96): a1, a2 in the bond frame (tensor_update.py:31-32), gate (d,d,d,d)
+    -> updated, normalised a1, a2 (still in the bond frame)."""
+    a1q, a1r, a2q, a2r = decompose_site_tensors(a1, a2)
+    n12 = norm_tensor(cell, bond, a1q, a2q)
+    a12g = torch.einsum("yup,xuq->yxpq", a1r, a2r)
+    a12g = torch.einsum("yxpq,pqrs->yxrs", a12g, gate)
+    nz = positive_approx(n12, cutoff=positive_approx_cutoff)
+    inv = (None, None)
+    if use_gauge_fix:
+        n12, a12g, nzxr_inv, nzyr_inv = gauge_fix(nz, a12g, atol=gauge_fix_atol)
+        inv = (nzxr_inv, nzyr_inv)
+    else:
+        n12 = torch.einsum("xyz,XYz->xyXY", nz, nz.conj())
+    b1, b2 = als_initial_guess(a12g, a1r.shape)
+    n12g = torch.einsum("yxYX,yxpq->YXpq", n12, a12g)
+    b1, b2, _ = als_solve(b1, b2, n12g, n12, a12g, niter=als_niter, tol=als_tol, epsilon=als_epsilon)
+    b1, b2 = finalize_reduced_tensors(b1, b2, *inv)
+    a1n, a2n = recompose_site_tensors(a1q, b1, a2q, b2)
+    return a1n / a1n.norm(), a2n / a2n.norm()
+
+
+def bond_theta(a1, a2):
+    """Gauge-invariant two-site tensor of a bond update result: a1's leg l contracted with a2's leg r (the legs the bond-frame
+    recomposition attaches the reduced tensors to, tensor_update.py:72-73); sign / rotation freedom on that leg cancels."""
+    return torch.einsum("burdp,LUbDq->urdpLUDq", a1, a2)
