@@ -164,7 +164,10 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
     const double* b_gp[B_CH];
     uint32_t b_so[B_CH];
     int b_nb[B_CH];
-    const int64_t a_kstep = (int64_t)BK * p.A.col.s_lo, b_kstep = (int64_t)BK * p.B.row.s_lo;
+    // k advance per tile: single-level k: BK * stride; two-level k whose div divides BK (and hence the split-K base): the low
+    // part of a thread's k never changes and the high part advances by BK / div per tile
+    const int64_t a_kstep = p.A.col.div ? (int64_t)(BK / (int)p.A.col.div) * p.A.col.s_hi : (int64_t)BK * p.A.col.s_lo;
+    const int64_t b_kstep = p.B.row.div ? (int64_t)(BK / (int)p.B.row.div) * p.B.row.s_hi : (int64_t)BK * p.B.row.s_lo;
     if (p.fast) {
         const int kbase = kt_begin * BK;
 #pragma unroll
@@ -176,7 +179,7 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
             int m = A_MC ? m0 + 2 * cp : m0 + r;
             int okc = A_MC ? (m + 1 < p.M ? 2 : (m < p.M ? 1 : 0)) : (m < p.M ? 1 : 0);
             int64_t fix = okc ? p.A.row.off(m) : 0;
-            a_gp[i] = Ab + fix + (int64_t)(kbase + klocal) * p.A.col.s_lo;
+            a_gp[i] = Ab + fix + p.A.col.off(kbase + klocal);
             a_nb[i] = (c < A_ROWS * A_CPR) ? (A_MC ? okc * 8 : (okc ? 16 : 0)) : -1;
         }
 #pragma unroll
@@ -188,7 +191,7 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
             int n = B_KC ? n0 + r : n0 + 2 * cp;
             int okc = B_KC ? (n < p.N ? 1 : 0) : (n + 1 < p.N ? 2 : (n < p.N ? 1 : 0));
             int64_t fix = okc ? p.B.col.off(n) : 0;
-            b_gp[i] = Bb + fix + (int64_t)(kbase + klocal) * p.B.row.s_lo;
+            b_gp[i] = Bb + fix + p.B.row.off(kbase + klocal);
             b_nb[i] = (c < B_ROWS * B_CPR) ? (B_KC ? (okc ? 16 : 0) : okc * 8) : -1;
         }
     }
@@ -476,7 +479,9 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     kp.A = d.A; kp.B = d.B; kp.C = d.C; kp.cm = d.cm; kp.cn = d.cn; kp.cb = d.cb;
     kp.alpha = d.alpha; kp.beta = d.beta;
     kp.a_vec = pl.a_vec; kp.b_vec = pl.b_vec;
-    kp.fast = (pl.a_vec && pl.b_vec && d.A.col.div == 0 && d.B.row.div == 0) ? 1 : 0;
+    // pointer-increment loader: both operands vectorisable and every k index either single level or two-level with div | BK
+    auto k_fast = [&](const Idx2& x) { return x.div == 0 || (x.div > 0 && x.div <= pl.bk && pl.bk % x.div == 0); };
+    kp.fast = (pl.a_vec && pl.b_vec && k_fast(d.A.col) && k_fast(d.B.row)) ? 1 : 0;
     kp.ws = nullptr;
     if (pl.splitk > 1) {
         size_t need = (size_t)d.M * d.N * d.batch * pl.splitk * sizeof(double);

@@ -565,7 +565,7 @@ def _als_solve_ar(R, S, epsilon):
     S = S.reshape(nD * bD, pD)
     R = R.reshape(nD * bD, nD * bD)
     R = 0.5 * (R + R.mH)
-    R = R + epsilon * R.abs().max() * torch.eye(R.shape[0], dtype=R.dtype)
+    R = R + epsilon * R.abs().max() * torch.eye(R.shape[0], dtype=R.dtype, device=R.device)
     L = torch.linalg.cholesky(R)
     Y = torch.linalg.solve_triangular(L, S, upper=False)
     return torch.linalg.solve_triangular(L.mH, Y, upper=True).reshape(nD, bD, pD)
@@ -630,7 +630,7 @@ def positive_approx(n12, cutoff=1e-12):
     N = n12.reshape(nD ** 2, nD ** 2).clone()
     nw, nz = torch.linalg.eigh(N)
     while nw[0] < cutoff:
-        N += 2 * max(cutoff, abs(float(nw[0]))) * torch.eye(nD ** 2, dtype=N.dtype)
+        N += 2 * max(cutoff, abs(float(nw[0]))) * torch.eye(nD ** 2, dtype=N.dtype, device=N.device)
         nw, nz = torch.linalg.eigh(N)
     return nz.reshape(nD, nD, nD ** 2) * torch.sqrt(nw)
 
