@@ -21,86 +21,94 @@ def _ix(*triples):
     return out
 
 
-def _norm_half(cA, eA, eB, cB, eC, aq, left):
-    """One half of the norm tensor (full_update.py:205-218 / 220-227):
-        right (left=False): n1[f,e,Y,y] = sum tmp_r2[a,f,d,D] ( ((c12 e12) e11) conj(a1q) a1q )[a,e,D,Y,d,y]
-        left  (left=True) : n2[f,c,X,x] = sum tmp_l2[b,f,d,D] ( ((c21 e21) e24) conj(a2q) a2q )[c,b,X,D,x,d]
-    Every leg permutation of the reference's einsum chain is folded into the two-level index descriptors of K1, so none of the
-    2 - 8 GiB intermediates is ever re-laid out in HBM (the generic gather + GEMM form spent 42 % of its time in gathers)."""
-    dev, dt = cA.device, cA.dtype
-    x0, x1 = cA.shape                      # cA[a,b]
-    xc, D = eA.shape[1], eA.shape[2]       # eA[b,c,.,.]
-    xe = eB.shape[0]                       # eB[e,a,.,.]
-    nD = aq.shape[3]
+def env_front(cA, eA, eB):
+    """t[(c,p,P),(e,q,Q)] = sum_{a,b} cA[a,b] eA[b,c,p,P] eB[e,a,q,Q]: the boundary part of a bond-environment half (full_update.py
+    :205-206 / :220-221, rdm.py:95-96 / :100-101), shared by everything that is contracted with site tensors afterwards."""
+    x0, x1 = cA.shape
+    xc, D = eA.shape[1], eA.shape[2]
+    xe = eB.shape[0]
     D2 = D * D
-    # 1. t1[a,(c,p,P)] = cA[a,b] eA[b,(c,p,P)]
-    t1 = ops.matmul(cA.contiguous(), eA.reshape(x1, xc * D2))
-    # 2. t[(c,p,P),(e,q,Q)] = sum_a t1[a,(c,p,P)] eB[e,a,(q,Q)]
-    m = xc * D2
-    n = xe * D2
-    t = torch.empty(m, n, dtype=dt, device=dev)
+    t1 = ops.matmul(cA.contiguous(), eA.contiguous().reshape(x1, xc * D2))            # t1[a,(c,p,P)]
+    m, n = xc * D2, xe * D2
+    t = torch.empty(m, n, dtype=cA.dtype, device=cA.device)
     ops.gemm_ex(m, n, x0, 1, t1, eB.contiguous(), t, _ix(1, m, 0, D2, (D2, x0 * D2, 1), 0, n, 1, 0))
-    del t1
-    # 3. t2[c,p,e,q,(n1,n2)] = sum_{P,Q} t[c,p,P,e,q,Q] aq[..]   (K = the two bra legs)
-    #    right: conj(a1q)[R,D,U,Y]: k=(R,U) n=(D,Y)      left: conj(a2q)[D,L,U,X]: k=(U,L) n=(X,D)
+    return t, (xc, xe, D)
+
+
+def env_back(t, dims, A5, bra, ket, Yb, yk, left):
+    """out[f, n-leg chi, Yb, yk] from t = env_front(...), the closing boundary A5[f][k-leg chi][(d,D)] and the site factors as
+    plain matrices:  bra[(P,Q)][Nb], ket[(p,q)][(d,yk)]  with  Nb enumerated (D,Yb) (right half) or (Yb,D) (left half).
+        right: k-leg = c (first chi leg of t), n-leg = e        left: k-leg = e, n-leg = c
+    Every leg permutation of the reference's einsum chain is folded into the two-level index descriptors of K1, so none of the
+    2 - 8 GiB intermediates is re-laid out in HBM (the generic gather + GEMM form spent 42 % of its time in gathers)."""
+    xc, xe, D = dims
+    dev, dt = t.device, t.dtype
+    D2 = D * D
+    n = xe * D2
+    Nb, Nk = D * Yb, D * yk
+    # 3. t2[c,p,e,q,Nb] = sum_{P,Q} t[c,p,P,e,q,Q] bra[(P,Q),Nb]
     M3 = xc * D * xe * D
-    N3 = D * nD
-    t2 = torch.empty(M3, N3, dtype=dt, device=dev)
-    a_m = (xe * D, D * n, D)               # hi = (c,p): stride D*n (= one p step), lo = (e,q): stride D
+    t2 = torch.empty(M3, Nb, dtype=dt, device=dev)
+    a_m = (xe * D, D * n, D)               # hi = (c,p): stride D*n, lo = (e,q): stride D
     a_k = (D, n, 1)                        # hi = P: stride n, lo = Q: stride 1
-    # the 64 KiB site factor as a plain (k, n) matrix for both steps (conj is the identity: FP64 real):
-    #   right: a1q[R,D,U,Y] -> [(R,U)][(D,Y)]      left: a2q[D,L,U,X] -> [(U,L)][(X,D)]
-    bq = (aq.permute(0, 2, 1, 3) if not left else aq.permute(2, 1, 3, 0)).contiguous()
-    ops.gemm_ex(M3, N3, D2, 1, t, bq, t2, _ix(a_m, a_k, 0, N3, 1, 0, N3, 1, 0))
-    del t
-    # 4. per (c,e): t3[(n1,n2),(n3,n4)] = sum_{p,q} t2[c,p,e,q,(n1,n2)] aq[..]   (K = the two ket legs), written straight into
-    #    the layout step 5 wants: [k-leg chi][d][D][n-leg chi][nD][nD]
-    #    right: a1q[r,d,u,y]: k=(r,u) n=(d,y), t3[c][d][D][e][Y][y]     left: a2q[d,l,u,x]: k=(u,l) n=(d,x), t3[e][d][D][c][X][x]
-    t3 = torch.empty(xc if not left else xe, D, D, xe if not left else xc, nD, nD, dtype=dt, device=dev)
-    s_e4, s_c4 = D * N3, D * xe * D * N3                              # strides of e and c in t2[c,p,e,q,N3]
+    ops.gemm_ex(M3, Nb, D2, 1, t, bra, t2, _ix(a_m, a_k, 0, Nb, 1, 0, Nb, 1, 0))
+    # 4. per (c,e): t3[Nb,(d,yk)] = sum_{p,q} t2[c,p,e,q,Nb] ket[(p,q),(d,yk)], written straight into the layout step 5 wants:
+    #    [k-leg chi][d][D][n-leg chi][Yb][yk]
+    kl, nl = (xc, xe) if not left else (xe, xc)
+    nn = Yb * yk
+    t3 = torch.empty(kl, D, D, nl, Yb, yk, dtype=dt, device=dev)
+    s_e4, s_c4 = D * Nb, D * xe * D * Nb                              # strides of e and c in t2[c,p,e,q,Nb]
     a_b = (xe, s_c4, s_e4)                                            # batch = (c,e)
-    a_k4 = (D, xe * D * N3, N3)                                       # k = (p,q)
-    nn = nD * nD
+    a_k4 = (D, xe * D * Nb, Nb)                                       # k = (p,q)
+    s_d, s_D, s_n, s_Y = D * nl * nn, nl * nn, nn, yk
     if not left:
-        kl, nl = xc, xe
-        s_d, s_D, s_n, s_Y = D * nl * nn, nl * nn, nn, nD             # t3[c][d][D][e][Y][y]
         c_b = (xe, D * D * nl * nn, s_n)                              # c -> k leg, e -> n leg
-        c_m = (nD, s_D, s_Y)                                          # m = (D,Y)
-        c_n = (nD, s_d, 1)                                            # n = (d,y)
+        c_m = (Yb, s_D, s_Y)                                          # m = (D,Yb)
     else:
-        kl, nl = xe, xc
-        s_d, s_D, s_n, s_X = D * nl * nn, nl * nn, nn, nD             # t3[e][d][D][c][X][x]
         c_b = (xe, s_n, D * D * nl * nn)                              # c -> n leg, e -> k leg
-        c_m = (D, s_X, s_D)                                           # m = (X,D)
-        c_n = (nD, s_d, 1)                                            # n = (d,x): x innermost => coalesced stores of the 8 GiB t3
-    bq4 = bq if not left else aq.permute(2, 1, 0, 3).contiguous()      # left: a2q[d,l,u,x] -> [(u,l)][(d,x)]
-    ops.gemm_ex(N3, N3, D2, xc * xe, t2, bq4, t3, _ix(1, a_k4, a_b, N3, 1, 0, c_m, c_n, c_b))
+        c_m = (D, s_Y, s_D)                                           # m = (Yb,D)
+    c_n = (yk, s_d, 1)                                                # n = (d,yk): yk innermost => coalesced stores
+    ops.gemm_ex(Nb, Nk, D2, xc * xe, t2, ket, t3, _ix(1, a_k4, a_b, Nk, 1, 0, c_m, c_n, c_b))
     del t2
-    # 5. out[f,(n-leg chi, nD, nD)] = sum_{k-leg chi, d, D} tmp2[k-leg chi, f, d, D] t3[(k-leg chi, d, D), (...)]
-    tmp2 = ops.matmul(cB.contiguous(), eC.reshape(cB.shape[1], -1)) if not left else None
-    if not left:
-        # tmp_r2[a,f,d,D] = c13[a,b] e13[b,f,d,D]
-        xf = eC.shape[1]
-        A5 = tmp2.reshape(cB.shape[0], xf, D2).permute(1, 0, 2).contiguous()          # [f][a][(d,D)]
-    else:
-        # tmp_l2[b,f,d,D] = c24[a,b] e23[f,a,d,D]
-        xf = eC.shape[0]
-        A5 = contract("ab,fadD->fbdD", cB, eC).contiguous()                             # [f][b][(d,D)]
+    # 5. out[f,(n-leg chi, Yb, yk)] = sum_{k-leg chi, d, D} A5[f,(k-leg chi, d, D)] t3[(k-leg chi, d, D), (...)]
+    xf = A5.shape[0]
     out = ops.matmul(A5.reshape(xf, kl * D2), t3.reshape(kl * D2, nl * nn))
-    return out.reshape(xf, nl, nD, nD)
+    return out.reshape(xf, nl, Yb, yk)
+
+
+def closing_right(cB, eC):
+    """tmp_r2[a,f,d,D] = cB[a,b] eC[b,f,d,D] (full_update.py:207, rdm.py:97) as A5[f][a][(d,D)]."""
+    D2 = eC.shape[2] * eC.shape[3]
+    xf = eC.shape[1]
+    return ops.matmul(cB.contiguous(), eC.contiguous().reshape(cB.shape[1], xf * D2)).reshape(cB.shape[0], xf, D2).permute(1, 0, 2).contiguous()
+
+
+def closing_left(cB, eC):
+    """tmp_l2[b,f,d,D] = cB[a,b] eC[f,a,d,D] (full_update.py:222, rdm.py:102) as A5[f][b][(d,D)]."""
+    return contract("ab,fadD->fbdD", cB, eC).contiguous()
 
 
 def build_norm_tensor(ipeps, bond, a1q, a2q):
-    """full_update.py:163-227 : N12[y,x,Y,X]; bond = (s1, s2, k); a1q/a2q (D,D,D,nD)."""
+    """full_update.py:163-227 : N12[y,x,Y,X]; bond = (s1, s2, k); a1q/a2q (D,D,D,nD).
+        right: n1[f,e,Y,y] = sum tmp_r2[a,f,d,D] ( ((c12 e12) e11) conj(a1q)[R,D,U,Y] a1q[r,d,u,y] )[a,e,D,Y,d,y]
+        left : n2[f,c,X,x] = sum tmp_l2[b,f,d,D] ( ((c21 e21) e24) conj(a2q)[D,L,U,X] a2q[d,l,u,x] )[c,b,X,D,x,d]"""
     s1, s2, k = bond
     a, b = ipeps[s1], ipeps[s2]
     c12, e12, e11 = a['C'][(k + 1) % 4], a['E'][(k + 1) % 4], a['E'][k % 4]
     c13, e13 = a['C'][(k + 2) % 4], a['E'][(k + 2) % 4]
     c21, e21, e24 = b['C'][k % 4], b['E'][k % 4], b['E'][(k + 3) % 4]
     c24, e23 = b['C'][(k + 3) % 4], b['E'][(k + 2) % 4]
-    a1q, a2q = a1q.contiguous(), a2q.contiguous()
-    n1 = _norm_half(c12, e12.contiguous(), e11, c13, e13.contiguous(), a1q, left=False)      # [f,e,Y,y]
-    n2 = _norm_half(c21, e21.contiguous(), e24, c24, e23.contiguous(), a2q, left=True)       # [f,c,X,x]
+    D, nD = a1q.shape[0], a1q.shape[3]
+    # the 64 KiB site factors as plain (k, n) matrices (conj is the identity: FP64 real)
+    q1 = a1q.permute(0, 2, 1, 3).contiguous().reshape(D * D, D * nD)                    # [(R,U)][(D,Y)] = [(r,u)][(d,y)]
+    t, dims = env_front(c12, e12, e11)
+    n1 = env_back(t, dims, closing_right(c13, e13), q1, q1, nD, nD, left=False)        # [f,e,Y,y]
+    del t
+    bra2 = a2q.permute(2, 1, 3, 0).contiguous().reshape(D * D, nD * D)                  # [(U,L)][(X,D)]
+    ket2 = a2q.permute(2, 1, 0, 3).contiguous().reshape(D * D, D * nD)                  # [(u,l)][(d,x)]
+    t, dims = env_front(c21, e21, e24)
+    n2 = env_back(t, dims, closing_left(c24, e23), bra2, ket2, nD, nD, left=True)      # [f,c,X,x]
+    del t
     return contract("fcYy,fcXx->yxYX", n1, n2).contiguous()
 
 

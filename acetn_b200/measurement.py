@@ -48,22 +48,29 @@ class RDM:
         a2 = b.bond_permute(k)
         d = a1.shape[-1]
 
-        tr1 = contract("ab,bcrR->acrR", c12, e12)
-        tr1 = contract("acrR,eauU->crReuU", tr1, e11)
-        tr2 = contract("ab,bfdD->afdD", c13, e13)
-        tl1 = contract("ab,bcuU->acuU", c21, e21)
-        tl1 = contract("acuU,ealL->cuUelL", tl1, e24)
-        tl2 = contract("ae,fadD->efdD", c24, e23)
-
-        right, left = [], []
+        # both halves through the gather-free environment contraction of the norm tensor (evolution.env_front / env_back): the
+        # bra site factor with its physical index fixed, the ket one with it open
+        #   right[P][f,c,L,(l,p)] = tmp_r2[a,f,d,D] (tr1 conj(a1)[L,U,R,D,P] a1[l,u,r,d,p])[a,c,L,D,l,d,p]      (rdm.py:95-99, 133-139)
+        #   left[Q][f,c,R,(r,q)]  = tmp_l2[e,f,d,D] (tl1 conj(a2)[L,U,R,D,Q] a2[l,u,r,d,q])[c,e,R,D,r,d,q]      (rdm.py:100-104, 141-147)
+        from .evolution import closing_left, closing_right, env_back, env_front
+        D = a1.shape[0]
+        D2 = D * D
+        ket1 = a1.permute(2, 1, 3, 0, 4).contiguous().reshape(D2, D * D * d)             # [(r,u)][(d,(l,p))]
+        ket2 = a2.permute(1, 0, 3, 2, 4).contiguous().reshape(D2, D * D * d)             # [(u,l)][(d,(r,q))]
+        tr, dims_r = env_front(c12, e12, e11)
+        A5r = closing_right(c13, e13)
+        right = []
         for P in range(d):
-            t = contract("crReuU,LURD->creuLD", tr1, a1[..., P].conj())
-            t = contract("creuLD,lurdp->ceLDldp", t, a1)
-            right.append(contract("afdD,acLDldp->fcLlp", tr2, t))        # [f,c,L,l,p]
+            bra = a1[..., P].permute(2, 1, 3, 0).contiguous().reshape(D2, D2)           # [(R,U)][(D,L)]
+            right.append(env_back(tr, dims_r, A5r, bra, ket1, D, D * d, left=False).reshape(A5r.shape[0], -1, D, D, d))
+        del tr
+        tl, dims_l = env_front(c21, e21, e24)
+        A5l = closing_left(c24, e23)
+        left = []
         for Q in range(d):
-            t = contract("cuUelL,LURD->cuelRD", tl1, a2[..., Q].conj())
-            t = contract("cuelRD,lurdq->ceRDrdq", t, a2)
-            left.append(contract("efdD,ceRDrdq->fcRrq", tl2, t))          # [f,c,R,r,q]
+            bra = a2[..., Q].permute(1, 0, 2, 3).contiguous().reshape(D2, D2)           # [(U,L)][(R,D)]
+            left.append(env_back(tl, dims_l, A5l, bra, ket2, D, D * d, left=True).reshape(A5l.shape[0], -1, D, D, d))
+        del tl
         rho = torch.empty(d, d, d, d, dtype=a1.dtype, device=a1.device)
         for P in range(d):
             for Q in range(d):
