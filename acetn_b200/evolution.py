@@ -13,6 +13,11 @@ from . import ops
 from .ops import contract
 
 
+import os as _os
+
+_SMALL_K_TILE = int(_os.environ.get("ACETN_B200_ENV_TILE", "0"))      # K1 tile of the K = D^2 steps (0 = planner's choice)
+
+
 def _ix(*triples):
     """27 ints of ops.gemm_ex: {div, s_hi, s_lo} for A(m, k, batch), B(k, n, batch), C(m, n, batch); a plain int is a stride."""
     out = []
@@ -51,7 +56,7 @@ def env_back(t, dims, A5, bra, ket, Yb, yk, left):
     t2 = torch.empty(M3, Nb, dtype=dt, device=dev)
     a_m = (xe * D, D * n, D)               # hi = (c,p): stride D*n, lo = (e,q): stride D
     a_k = (D, n, 1)                        # hi = P: stride n, lo = Q: stride 1
-    ops.gemm_ex(M3, Nb, D2, 1, t, bra, t2, _ix(a_m, a_k, 0, Nb, 1, 0, Nb, 1, 0))
+    ops.gemm_ex(M3, Nb, D2, 1, t, bra, t2, _ix(a_m, a_k, 0, Nb, 1, 0, Nb, 1, 0), force_tile=_SMALL_K_TILE)
     # 4. per (c,e): t3[Nb,(d,yk)] = sum_{p,q} t2[c,p,e,q,Nb] ket[(p,q),(d,yk)], written straight into the layout step 5 wants:
     #    [k-leg chi][d][D][n-leg chi][Yb][yk]
     kl, nl = (xc, xe) if not left else (xe, xc)
@@ -68,7 +73,7 @@ def env_back(t, dims, A5, bra, ket, Yb, yk, left):
         c_b = (xe, s_n, D * D * nl * nn)                              # c -> n leg, e -> k leg
         c_m = (D, s_Y, s_D)                                           # m = (Yb,D)
     c_n = (yk, s_d, 1)                                                # n = (d,yk): yk innermost => coalesced stores
-    ops.gemm_ex(Nb, Nk, D2, xc * xe, t2, ket, t3, _ix(1, a_k4, a_b, Nk, 1, 0, c_m, c_n, c_b))
+    ops.gemm_ex(Nb, Nk, D2, xc * xe, t2, ket, t3, _ix(1, a_k4, a_b, Nk, 1, 0, c_m, c_n, c_b), force_tile=_SMALL_K_TILE)
     del t2
     # 5. out[f,(n-leg chi, Yb, yk)] = sum_{k-leg chi, d, D} A5[f,(k-leg chi, d, D)] t3[(k-leg chi, d, D), (...)]
     xf = A5.shape[0]
