@@ -138,6 +138,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is the CPU path on ALL host cores of the box
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     times = []
     on_gpu = args.ref_device == "cuda"
     for i in range(args.warmup + args.steps):
