@@ -1,0 +1,46 @@
+"""CPU tests of bench.py's contract: the reference arm (`--impl reference`, the oracle port of the reference's CPU torch path)
+prints exactly one JSON line with the keys the driver reads, uses all host cores even when the launcher exported
+OMP_NUM_THREADS=1 (torchrun does), and non-zero ranks exit without work; the product arm refuses to run without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e, timeout=600)
+
+
+def test_reference_arm_line():
+    r = _run(["--impl", "reference", "--D", "2", "--chi", "6", "--steps", "1", "--warmup", "1"], env={"OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["cores"] == ncpu          # not the launcher's OMP_NUM_THREADS=1
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    r = _run(["--impl", "reference", "--gpus", "2", "--D", "2", "--chi", "6", "--steps", "1", "--warmup", "1"],
+             env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_arm_needs_a_gpu():
+    r = _run(["--D", "2", "--chi", "6", "--steps", "1", "--warmup", "1"])
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
