@@ -43,6 +43,10 @@ SIGNATURES = {
     "acetn_b200_absorb_corner2": (c_int, [c_vp, c_vp, c_vp] + [c_i64] * 5 + [c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_absorb_edge_workspace_bytes": (c_sz, [c_i64] * 6),
     "acetn_b200_absorb_edge": (c_int, [c_vp, c_vp, P_i64, c_vp, c_vp] + [c_i64] * 6 + [c_int, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_absorb_edge_begin_workspace_bytes": (c_sz, [c_i64] * 5),
+    "acetn_b200_absorb_edge_begin": (c_int, [c_vp, c_vp, P_i64, c_vp] + [c_i64] * 5 + [c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_absorb_edge_finish_workspace_bytes": (c_sz, [c_i64] * 4),
+    "acetn_b200_absorb_edge_finish": (c_int, [c_vp, c_vp] + [c_i64] * 4 + [c_int, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_double_layer_workspace_bytes": (c_sz, [c_i64] * 4),
     "acetn_b200_double_layer": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, P_i64, c_int, c_vp, P_i64, c_i64, c_i64, c_vp, c_i64,
                                         c_i64, P_i64, c_vp, c_sz, c_vp]),

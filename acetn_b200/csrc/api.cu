@@ -543,6 +543,60 @@ int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_s
     return frob_normalize_launch(out, (size_t)(xy * xx * D2), fs, s);
 }
 
+// ---- the edge absorption in two stages, so that a scheduler can run the part that only needs proj1 of the neighbouring task
+//      (2 chi^3 D^4 + 4 chi^2 D^6 d of the 4 chi^3 D^4 + 4 chi^2 D^6 d flops) before this task's own projector pair exists:
+//        begin : T3[a,(d,Dd),x,(r,R)] = sum ei[a,b,l,L] proj1[b,u,U,x] conj(A)[L,U,R,Dd,P] A[l,u,r,d,P]     (T3: chi_a chi_x D^4 doubles)
+//        finish: out[y,x,r,R] = sum proj2[a,d,Dd,y] T3[a,(d,Dd),x,(r,R)],  Frobenius-normalised if normalize != 0
+//      Same kernels, same launch parameters and same order per output element as acetn_b200_absorb_edge: bit-identical results.
+size_t acetn_b200_absorb_edge_begin_workspace_bytes(int64_t xa, int64_t xb, int64_t xx, int64_t D, int64_t d) {
+    EdgeDims e{xa, xb, xx, 1, D, d};
+    const int64_t D2 = D * D, D4 = D2 * D2;
+    size_t b = ws_round((size_t)(xb * xx * D2) * 8) + ws_round((size_t)(xa * xx * D4) * 8);
+    return b + maxz(gemm_workspace_bytes(e_g1(e, nullptr, nullptr, nullptr)), dl_workspace_bytes(xa, xx, D, d)) + 4096;
+}
+int acetn_b200_absorb_edge_begin(const double* ei, const double* A, const int64_t* a_strides, const double* proj1, int64_t xa, int64_t xb,
+                                 int64_t xx, int64_t D, int64_t d, double* T3, void* wsp, size_t ws_bytes, void* stream) {
+    cudaStream_t s = S_(stream);
+    EdgeDims e{xa, xb, xx, 1, D, d};
+    const int64_t D2 = D * D, D4 = D2 * D2;
+    AB_REQUIRE(xa * D2 < 2147483647LL && xx * D2 < 2147483647LL, "absorb_edge_begin: chi*D^2 too large");
+    Workspace ws(wsp, ws_bytes);
+    double* P1t = ws.take<double>((size_t)(xb * xx * D2));
+    double* T = ws.take<double>((size_t)(xa * xx * D4));
+    if (ws.overflow) { set_error("absorb_edge_begin: workspace too small (%zu needed, %zu given)", ws.used, ws_bytes); return ERR_WORKSPACE; }
+    void* g = ws.base + ws.used; size_t gb = ws.bytes - ws.used;
+    {   // P1t[b,x,(uU)] = proj1[b,(uU),x]
+        int64_t dims[5] = {xb, xx, D2, 1, 1};
+        int64_t st[5] = {D2 * xx, 1, xx, 0, 0};
+        AB_TRY(gather5_launch(P1t, proj1, dims, st, s));
+    }
+    AB_TRY(gemm_launch(e_g1(e, ei, P1t, T), g, gb, s));             // T[a,x,(l,L),(u,U)]
+    DoubleLayerArgs a;
+    a.X = T; a.n0 = xa; a.n1 = xx; a.in_s0 = xx * D4; a.in_s1 = D4;
+    a.in_es[0] = D2 * D; a.in_es[1] = D2; a.in_es[2] = D; a.in_es[3] = 1;   // (l,L,u,U)
+    a.order = 1; a.A = A; a.D = D; a.d = d;
+    a.Y = T3; a.out_s0 = D2 * xx * D2; a.out_s1 = D2;                       // T3[a,(d,Dd),x,(r,R)]
+    a.out_es[0] = D; a.out_es[1] = 1; a.out_es[2] = D * xx * D2; a.out_es[3] = xx * D2;
+    for (int i = 0; i < 5; i++) a.a_s[i] = a_strides[i];
+    return double_layer(a, nullptr, g, gb, s);
+}
+size_t acetn_b200_absorb_edge_finish_workspace_bytes(int64_t xa, int64_t xx, int64_t xy, int64_t D) {
+    EdgeDims e{xa, 1, xx, xy, D, 1};
+    return ws_round(frob_scratch_doubles() * 8) + gemm_workspace_bytes(e_g4(e, nullptr, nullptr, nullptr)) + 4096;
+}
+int acetn_b200_absorb_edge_finish(const double* proj2, const double* T3, int64_t xa, int64_t xx, int64_t xy, int64_t D, int normalize,
+                                  double* out, void* wsp, size_t ws_bytes, void* stream) {
+    cudaStream_t s = S_(stream);
+    EdgeDims e{xa, 1, xx, xy, D, 1};
+    Workspace ws(wsp, ws_bytes);
+    double* fs = ws.take<double>(frob_scratch_doubles());
+    if (ws.overflow) { set_error("absorb_edge_finish: workspace too small"); return ERR_WORKSPACE; }
+    void* g = ws.base + ws.used; size_t gb = ws.bytes - ws.used;
+    AB_TRY(gemm_launch(e_g4(e, proj2, T3, out), g, gb, s));        // out[y,(x,r,R)]
+    if (!normalize) return OK;
+    return frob_normalize_launch(out, (size_t)(xy * xx * D * D), fs, s);
+}
+
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream) { return dmma_peak_launch((double*)scratch, iters, S_(stream)); }
 
 size_t acetn_b200_als_workspace_bytes(int64_t nD, int64_t bD, int64_t pD) { return als_workspace_bytes((int)nD, (int)bD, (int)pD); }

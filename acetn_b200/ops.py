@@ -280,6 +280,43 @@ def absorb_edge(ei, A_view, proj2, proj1, normalize=True):
     return out
 
 
+def absorb_edge_begin(ei, A_view, proj1):
+    """First stage of absorb_edge (needs only proj1 of the neighbouring task): T3[a,(d,Dd),x,(r,R)], see include/acetn_b200.h."""
+    dev = _require_cuda(ei, A_view, proj1)
+    ei, proj1 = ei.contiguous(), proj1.contiguous()
+    xa, xb, D = ei.shape[0], ei.shape[1], ei.shape[2]
+    d = A_view.shape[4]
+    xx = proj1.shape[3]
+    if proj1.shape[0] != xb:
+        raise ValueError("absorb_edge_begin: inconsistent chi legs")
+    lib = _lib.load()
+    T3 = torch.empty(xa * D * D, xx * D * D, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_absorb_edge_begin_workspace_bytes(xa, xb, xx, D, d))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_absorb_edge_begin(_p(ei), _p(A_view), _lib.i64_array(A_view.stride()), _p(proj1), xa, xb, xx, D, d, _p(T3),
+                                              _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "absorb_edge_begin")
+    return T3
+
+
+def absorb_edge_finish(T3, proj2, D, normalize=True):
+    """Second stage of absorb_edge: out[y,x,r,R] = sum proj2[a,d,Dd,y] T3[a,(d,Dd),x,(r,R)] (+ Frobenius normalisation)."""
+    dev = _require_cuda(T3, proj2)
+    proj2 = proj2.contiguous()
+    xa, xy = proj2.shape[0], proj2.shape[3]
+    xx = T3.shape[1] // (D * D)
+    if T3.shape[0] != xa * D * D:
+        raise ValueError("absorb_edge_finish: inconsistent chi legs")
+    lib = _lib.load()
+    out = torch.empty(xy, xx, D, D, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_absorb_edge_finish_workspace_bytes(xa, xx, xy, D))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_absorb_edge_finish(_p(proj2), _p(T3), xa, xx, xy, D, 1 if normalize else 0, _p(out), _p(ws), ws.numel(),
+                                               _stream(dev))
+    _lib.check(st, "absorb_edge_finish")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # generic pairwise contraction (transpose-transpose-GEMM): used by the measure / norm-tensor paths
 # ---------------------------------------------------------------------------------------------------------------

@@ -131,6 +131,17 @@ int acetn_b200_absorb_edge(const double* ei, const double* A, const int64_t* a_s
                            const double* proj1, int64_t chi_a, int64_t chi_b, int64_t chi_x, int64_t chi_y, int64_t D,
                            int64_t d, int normalize, double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* The edge absorption in two stages (same kernels and launch parameters as acetn_b200_absorb_edge => bit-identical): `begin` needs
+ * only proj1 of the neighbouring task and produces T3 (chi_a * chi_x * D^4 doubles, caller-owned); `finish` contracts it with
+ * this task's proj2 (directional_mover.py:362-366).  Lets a scheduler start most of the absorption before the last projector pair
+ * of a move exists. */
+size_t acetn_b200_absorb_edge_begin_workspace_bytes(int64_t chi_a, int64_t chi_b, int64_t chi_x, int64_t D, int64_t d);
+int acetn_b200_absorb_edge_begin(const double* ei, const double* A, const int64_t* a_strides, const double* proj1, int64_t chi_a,
+                                 int64_t chi_b, int64_t chi_x, int64_t D, int64_t d, double* T3, void* ws, size_t ws_bytes, void* stream);
+size_t acetn_b200_absorb_edge_finish_workspace_bytes(int64_t chi_a, int64_t chi_x, int64_t chi_y, int64_t D);
+int acetn_b200_absorb_edge_finish(const double* proj2, const double* T3, int64_t chi_a, int64_t chi_x, int64_t chi_y, int64_t D,
+                                  int normalize, double* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- double-layer site absorption on its own (K2; the `cuUelL,LURDP->cuelRDP` + `lurdp,cuelRDp->crRedD` pair of
  *      projectors.py:54-55 and the matching pair of directional_mover.py:363-364), exposed for tests/benchmarks.
  *   in : X[b0, (i0,I0), b1, (i1,I1)] with block (b0,b1) at  b0*in_s0 + b1*in_s1 and element strides in_es[4] for
