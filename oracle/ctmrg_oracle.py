@@ -13,7 +13,9 @@ Parity status: PINNED.  tests/test_oracle_golden.py checks this restatement agai
        tests/golden/make_golden.py), and
   (ii) golden vectors produced by importing the reference itself in the build container
        (tests/golden/make_golden.py: quarter tensors, rSVD spectra with recorded Omega,
-       projectors, absorbed C/E, RDMs, energies after sweeps).
+       projectors, absorbed C/E, RDMs, energies after sweeps), and
+  (iii) the reference's norm tensor, ALS iterates and whole FullUpdater.tensor_update outputs
+       (tests/golden/make_golden_fu.py -> ref_vectors_fu.pt; reproduced bit for bit).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  Conventions: A[l,u,r,d,p]; k: 0=left 1=up 2=right
