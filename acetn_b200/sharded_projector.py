@@ -20,12 +20,23 @@ import torch
 import torch.distributed as dist
 
 
-class B200LinAlg:
-    """libacetn_b200.so kernels."""
+class _EncodedRows:
+    """Row block of a quarter tensor together with its K7 encoding (int8 residue planes); quacks like the matrix for `.shape`."""
 
-    def __init__(self):
+    def __init__(self, Q, enc):
+        self.Q, self.enc, self.shape = Q, enc, Q.shape
+
+
+class B200LinAlg:
+    """libacetn_b200.so kernels.  use_i8 (default: env ACETN_B200_COOP_I8 == "1", EXPERIMENTAL -- written for the next round, not
+    yet measured on multi-GPU boxes): the row blocks are encoded once and every big x thin product of the cooperative rSVD
+    runs on K7 (exact integer arithmetic on the INT8 tensor cores) like in the single-rank path."""
+
+    def __init__(self, use_i8=None):
+        import os
         from . import ops
         self.ops = ops
+        self.use_i8 = (os.environ.get("ACETN_B200_COOP_I8", "0") == "1") if use_i8 is None else bool(use_i8)
 
     def quarter_rows(self, site_tensor, k, c0, c1, absmax):
         ak = site_tensor.bond_permute(k)
@@ -33,9 +44,15 @@ class B200LinAlg:
         ek1 = site_tensor['E'][(3 + k) % 4]
         ek2 = site_tensor['E'][k % 4][:, c0:c1].contiguous()
         Q, shp = self.ops.quarter_tensor(ck, ek2, ek1, ak, normalize=False, absmax=absmax)
+        if self.use_i8 and min(Q.shape) >= 4096 and self.ops.i8_supported(Q.shape[0], Q.shape[1], 272):
+            return _EncodedRows(Q, self.ops.i8_encode(Q))
         return Q
 
     def matmul(self, A, B, transpose_a=False, out=None):
+        if isinstance(A, _EncodedRows):
+            if B.shape[1] <= 272:
+                return self.ops.i8_matmul(A.enc, B.contiguous(), adjoint=transpose_a, out=out)
+            A = A.Q
         return self.ops.matmul(A, B, transpose_a=transpose_a, out=out)
 
     def orthonormalize(self, Y):
