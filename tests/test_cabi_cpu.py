@@ -55,6 +55,11 @@ def test_workspace_queries_run_without_gpu(lib):
     assert lib.acetn_b200_rsvd_workspace_bytes(2, rows, cols, 258) > 5 * 16384 * 258 * 8
     assert lib.acetn_b200_orthonormalize_workspace_bytes(16384, 258) > 0
     assert lib.acetn_b200_jacobi_svd_workspace_bytes(258) >= 2 * 258 * 258 * 8
+    # the two-stage edge absorption: stage 1 holds P1t + T (2 GiB at D=8 chi=256), stage 2 only GEMM / normalisation scratch
+    full = lib.acetn_b200_absorb_edge_workspace_bytes(256, 256, 256, 256, 8, 2)
+    begin = lib.acetn_b200_absorb_edge_begin_workspace_bytes(256, 256, 256, 8, 2)
+    finish = lib.acetn_b200_absorb_edge_finish_workspace_bytes(256, 256, 256, 8)
+    assert 2 * 2**30 < begin < full and finish < 2**30
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
