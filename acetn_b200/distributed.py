@@ -36,10 +36,10 @@ class _Null:
 class B200Compute:
     """Default backend: libacetn_b200.so through acetn_b200.renormalization."""
 
-    def __init__(self, config):
+    def __init__(self, config, mover=None):
         self.config = config
         from .renormalization import DirectionalMover
-        self.mover = DirectionalMover(config)
+        self.mover = mover if mover is not None else DirectionalMover(config)
         self.pc = self.mover.projector_calculator
 
     def tasks(self, ipeps, k, line):
@@ -58,23 +58,23 @@ class B200Compute:
         if group_size <= 1 and len(tasks) > 1 and self.mover.staggered():
             # several tasks on this rank: quarter tensors + encodings in task order on the low-priority bulk stream, every rSVD
             # chain on its own high-priority stream (renormalization.DirectionalMover.move_pair)
-            bulk, streams = self.mover.phase_streams(device, len(tasks))
+            bulk, streams = self.mover.phase_streams(device, min(len(tasks), self.mover.inflight))
             for st in streams + [bulk]:
                 st.wait_stream(main)
-            pend = [self.pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n], bulk=bulk)
-                    for n, t in enumerate(tasks)]
-            out = [self.pc.finish(pd) for pd in pend]
+            retired = []
+            out = [res for _, _, res in self.mover._pipeline(ipeps, [(t["plaq"], t["k"]) for t in tasks], omegas, streams, retired, bulk)]
             for st in streams + [bulk]:
                 main.wait_stream(st)
-            del pend
+            del retired
             return [(a.contiguous(), b.contiguous()) for a, b in out]
         streams = self.mover._side_streams(device)
         for st in streams:
             if st is not None:
                 st.wait_stream(main)
+        pend = None
         if group_size <= 1:
-            pend = [self.pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n]) for n, t in enumerate(tasks)]
-            out = [self.pc.finish(pd) for pd in pend]
+            pend = []
+            out = [res for _, _, res in self.mover._pipeline(ipeps, [(t["plaq"], t["k"]) for t in tasks], omegas, streams, pend)]
         else:
             from .sharded_projector import ShardedHalfSystemProjector
             sp = ShardedHalfSystemProjector(self.mover.projector_calculator, group, group_rank, group_size)

@@ -13,6 +13,10 @@
     acetn_b200.renormalization.ctmrg, anything else to the untouched reference function (which stays the oracle path);
   * `acetn.evolution.full_update.FullUpdater.tensor_update` (one bond update: QR split, norm tensor, positive_approx,
     gauge_fix, ALS, finalisation) routes to `acetn_b200.evolution.full_update_bond` for backend "b200";
+  * `acetn.evolution.fast_full_update.FastFullUpdater` (what `ipeps.evolve` builds for update_type="full", evolve.py:11-15): its
+    `mover` (fast_full_update.py:27) becomes `acetn_b200.renormalization.DirectionalMover`, and `absorb_bond` /
+    `absorb_bond_dist` (:72-129) -- the two CTMRG moves after EVERY bond update, which dominate `evolve` --
+    route to `DirectionalMover.absorb_bond` / the site-sharded phases of acetn_b200.distributed;
   * `acetn.renormalization.projectors.{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}` are NOT replaced
     globally: backend "torch" keeps the reference numerics bit for bit.
 The reference's SiteTensor / TensorNetwork objects are used as they are: the B200 mover only needs `ipeps[site]['A'|'C'|'E']`,
@@ -112,5 +116,33 @@ def install(acetn_module=None):
         return ref_tensor_update(self, a1, a2, bond)
 
     fu_mod.FullUpdater.tensor_update = tensor_update
+
+    # ---- evolve: the CTMRG moves that absorb every updated bond (fast_full_update.py:27, 72-129) ----------------------------
+    import acetn.evolution.fast_full_update as ffu_mod
+    FFU = ffu_mod.FastFullUpdater
+    ref_ffu_init, ref_absorb, ref_absorb_dist = FFU.__init__, FFU.absorb_bond, FFU.absorb_bond_dist
+
+    def ffu_init(self, ipeps, gate, config):
+        ref_ffu_init(self, ipeps, gate, config)
+        if getattr(config, "backend", "torch") == "b200":
+            self.mover = b200_renorm.DirectionalMover(ipeps.config.ctmrg)
+
+    @ffu_mod.record_runtime
+    def b200_absorb(self, bond):
+        self.mover.absorb_bond(self.ipeps, bond)
+
+    def absorb_bond(self, bond):
+        if self.backend == "b200":
+            return b200_absorb(self, bond)
+        return ref_absorb(self, bond)
+
+    def absorb_bond_dist(self, bond):
+        # the reference's body (mover.left_right_move_dist / up_down_move_dist, :117-129) runs unchanged: for backend "b200" the
+        # mover is the B200 one, whose *_dist moves are the site-sharded phases of acetn_b200.distributed.ShardedCtmrg
+        return ref_absorb_dist(self, bond)
+
+    FFU.__init__ = ffu_init
+    FFU.absorb_bond = absorb_bond
+    FFU.absorb_bond_dist = absorb_bond_dist
     ipeps_mod._acetn_b200_installed = True
     return acetn_module

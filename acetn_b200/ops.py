@@ -25,6 +25,12 @@ def _require_cuda(*tensors):
     return dev
 
 
+def require_cuda_device(device):
+    """The host mirrors call this before scheduling work: backend='b200' has no CPU path."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+
+
 def _ws(dev, nbytes, stream=None):
     """Per-(device, stream) grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
     # one scratch buffer per CUDA stream: work enqueued on different streams may run concurrently
@@ -100,9 +106,10 @@ def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0, out=None):
     return gemm_ex(M, N, K, 1, A, B, C, idx, force_tile=force_tile, force_splitk=force_splitk)
 
 
-def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None):
+def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, out=None):
     """projectors.py:36-60.  C (xa,xb), E2 (xb,xc,D,D), E1 (xe,xa,D,D), A_view = bond_permute(k) (strided view).
-    absmax: optional 1-element device tensor receiving max|Q| of the un-normalised tensor."""
+    absmax: optional 1-element device tensor receiving max|Q| of the un-normalised tensor.
+    out: optional flat FP64 device buffer (>= numel of Q) that receives Q (a task slot of the phase scheduler)."""
     dev = _require_cuda(C, E2, E1, A_view)
     C, E2, E1 = C.contiguous(), E2.contiguous(), E1.contiguous()
     xa, xb = C.shape
@@ -112,7 +119,10 @@ def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None):
     if E2.shape[0] != xb or E1.shape[1] != xa:
         raise ValueError(f"quarter_tensor: inconsistent chi legs C{tuple(C.shape)} E2{tuple(E2.shape)} E1{tuple(E1.shape)}")
     lib = _lib.load()
-    Q = torch.empty(xc * D * D, xe * D * D, dtype=torch.float64, device=dev)
+    if out is not None:
+        Q = out[:xc * D * D * xe * D * D].view(xc * D * D, xe * D * D)
+    else:
+        Q = torch.empty(xc * D * D, xe * D * D, dtype=torch.float64, device=dev)
     nb = lib.acetn_b200_quarter_tensor_workspace_bytes(xa, xb, xc, xe, D, d)
     ws = _ws(dev, nb, stream)
     with torch.cuda.device(dev):
@@ -431,6 +441,10 @@ class I8Encoded:
 
 def i8_supported(rows, cols, q):
     return bool(_lib.load().acetn_b200_i8_supported(rows, cols, q))
+
+
+def i8_encoded_bytes(rows, cols):
+    return int(_lib.load().acetn_b200_i8_encoded_bytes(rows, cols))
 
 
 def i8_encode(Q, stream=None, storage=None):

@@ -44,7 +44,7 @@ class ProjectorCalculator:
             raise ValueError(f"Invalid ctmrg projector type: {self.projectors} provided.")
 
     @staticmethod
-    def make_quarter_tensor(site_tensor, k, normalize=True, stream=None, absmax=None):
+    def make_quarter_tensor(site_tensor, k, normalize=True, stream=None, absmax=None, out=None):
         """projectors.py:36-60 -> (Q matrix (chi D^2, chi D^2), 6-tuple shape).
         normalize=False skips the max-abs division (projectors.py:59): s/s[0], U and V are invariant under a rescaling
         of Q1/Q4, and the internal callers re-apply the factor 1/max|Q| to the small projector instead (absmax), which
@@ -53,7 +53,13 @@ class ProjectorCalculator:
         ck = site_tensor['C'][(0 + k) % 4]
         ek1 = site_tensor['E'][(3 + k) % 4]
         ek2 = site_tensor['E'][(0 + k) % 4]
-        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax)
+        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax, out=out)
+
+    @staticmethod
+    def quarter_numel(site_tensor, k):
+        """Number of elements of make_quarter_tensor(site_tensor, k): (chi_c D^2) x (chi_e D^2)."""
+        D = site_tensor['A'].shape[0]
+        return site_tensor['E'][(0 + k) % 4].shape[1] * site_tensor['E'][(3 + k) % 4].shape[0] * D ** 4
 
     I8_MIN_DIM = 4096        # "auto": quarter tensors at least this large go through K7
 
@@ -129,12 +135,14 @@ class ProjectorCalculator:
         return self._full_rank_projectors(R1, R2, F, d1, d4, ipeps.dims["chi"])
 
     # ---- phase 1 ------------------------------------------------------------------------------------------------
-    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None):
+    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None, slot=None):
         """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed).
         bulk: optional second CUDA stream for the throughput-bound first stage (quarter tensors + their K7 encodings); the rSVD
         chain (K7 products interleaved with ~500 latency-bound TSQR / Jacobi launches) then runs on `stream`, ordered behind
         the first stage by an event.  DirectionalMover.move_pair passes one low-priority bulk stream for all tasks of a phase
-        and a high-priority `stream` per task."""
+        and a high-priority `stream` per task.
+        slot: optional TaskSlot whose grow-only buffers receive the two quarter tensors and their K7 encodings, so that a phase
+        with more tasks than slots re-uses them instead of holding every task's 12 GiB until the phase ends."""
         self._check_svd_type()
         if self.svd_type == "full-rank":
             return {"kind": "done", "result": self._full_rank_half_system(ipeps, sites, k), "stream": None}
@@ -145,12 +153,16 @@ class ProjectorCalculator:
             omega = self.draw_omega(ipeps, sites, k)
         sa = bulk if (bulk is not None and stream is not None) else stream
         mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
-        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1])
-        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2])
+        o1 = slot.buffer("Q1", self.quarter_numel(st1, k), omega.dtype, omega.device) if slot is not None else None
+        o4 = slot.buffer("Q4", self.quarter_numel(st4, k + 3), omega.dtype, omega.device) if slot is not None else None
+        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1], out=o1)
+        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2], out=o4)
         encs = None
         if self._use_i8([tuple(Q1.shape), tuple(Q4.shape)], omega.shape[1]):
             # K7: both quarter tensors are encoded once (16 int8 residue planes) and serve all 13 thin products
-            encs = [ops.i8_encode(Q1, stream=sa), ops.i8_encode(Q4, stream=sa)]
+            s1b = slot.buffer("enc1", ops.i8_encoded_bytes(*Q1.shape), torch.uint8, omega.device) if slot is not None else None
+            s4b = slot.buffer("enc4", ops.i8_encoded_bytes(*Q4.shape), torch.uint8, omega.device) if slot is not None else None
+            encs = [ops.i8_encode(Q1, stream=sa, storage=s1b), ops.i8_encode(Q4, stream=sa, storage=s4b)]
         if sa is not stream:
             built = torch.cuda.Event()
             built.record(sa)
@@ -161,7 +173,7 @@ class ProjectorCalculator:
         return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": None, "S": S, "V": V, "info": info,
                 "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream, "encs": encs}
 
-    def begin_full_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None):
+    def begin_full_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None, slot=None):
         """projectors.py:176-201 : rSVD of (Q2 Q1)(Q4 Q3)."""
         self._check_svd_type()
         if self.svd_type == "full-rank":
@@ -249,6 +261,27 @@ class ProjectorCalculator:
         return self.finish(self.begin_full_system(ipeps, sites, k))
 
 
+class TaskSlot:
+    """Grow-only device buffers of one in-flight projector task (two quarter tensors + their K7 encodings = 12 GiB at D=8,
+    chi=256).  A phase with more tasks than slots re-uses a slot once the previous task's projector pair is complete (`ready`),
+    so peak memory is bounded by the window, not by the number of tasks of the phase (the reference holds one projector's
+    quarter tensors at a time, projectors.py:138-161)."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.ready = None        # event: the last task that used this slot has finished reading its buffers
+
+    def buffer(self, name, numel, dtype, device):
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype or buf.device != device:
+            if buf is not None:
+                torch.cuda.synchronize(device)       # rare (chi still growing): kernels of a side stream may still read the old one
+            self.bufs[name] = None
+            buf = torch.empty(int(numel), dtype=dtype, device=device)
+            self.bufs[name] = buf
+        return buf
+
+
 class DirectionalMover:
     """acetn/renormalization/directional_mover.py:5-366 (non-distributed moves).
 
@@ -268,6 +301,11 @@ class DirectionalMover:
         # latency-bound launches of a chain (TSQR, Jacobi, CRT) ahead of the pending CTAs of the next task's DGEMMs instead
         # of queueing them behind whole 4 ms kernels, and the tasks no longer go through their latency-bound stages in lockstep.
         self.stagger = os.environ.get("ACETN_B200_STAGGER", "1") != "0"
+        # at most this many projector tasks are begun-but-unfinished at any time (each holds 2 quarter tensors + encodings)
+        self.inflight = max(1, int(os.environ.get("ACETN_B200_INFLIGHT", "4")))
+        self._slots = []
+        self._config = config
+        self._sharded = None
         self.split_edge = os.environ.get("ACETN_B200_SPLIT_EDGE", "1") != "0"     # piecewise absorptions (see _finish_and_absorb_piecewise)
 
     def _side_streams(self, device):
@@ -293,27 +331,61 @@ class DirectionalMover:
             self._hi_streams.append(torch.cuda.Stream(device=device, priority=-1))
         return self._bulk_stream, self._hi_streams[:n]
 
+    def release(self):
+        """Drop the task-slot buffers (they are re-created on demand)."""
+        self._slots = []
+
+    def _pipeline(self, ipeps, specs, omegas, streams, retired, bulk=None):
+        """Generator over the projector tasks specs = [(sites, k)]: yields (n, pending, (proj1, proj2)) in task order while at most
+        `inflight` tasks are begun-but-unfinished.  Task n + W is begun (on the slot of task n) when the consumer asks for the next
+        item, i.e. after it has queued whatever it derives from task n -- same kernels in the same per-tensor order for any W.
+        retired: caller-owned list that keeps the small per-task tensors (Omega, S, V, AtQ, ...) alive until the caller has
+        ordered its main stream behind the side streams; only the 12 GiB of a task slot are recycled inside a phase."""
+        pc = self.projector_calculator
+        W = max(1, min(self.inflight, len(specs)))
+        while len(self._slots) < W:
+            self._slots.append(TaskSlot())
+        pend = {}
+
+        def begin(n):
+            sites, k = specs[n]
+            slot = self._slots[n % W]
+            stream = streams[n % len(streams)]
+            first = bulk if (bulk is not None and stream is not None) else stream
+            if slot.ready is not None and first is not None:
+                first.wait_event(slot.ready)
+            pend[n] = pc.begin(ipeps, sites, k, stream=stream, omega=omegas[n], bulk=bulk, slot=slot)
+
+        for n in range(W):
+            begin(n)
+        for n in range(len(specs)):
+            pd = pend.pop(n)
+            res = pc.finish(pd)
+            self._slots[n % W].ready = pd.get("ready")
+            retired.append(pd)
+            yield n, pd, res
+            del pd
+            if n + W < len(specs):
+                begin(n + W)
+
     def _projectors_of_line(self, ipeps, plaquettes, k):
         """All projector pairs of one move: {key: (proj1, proj2)} ; plaquettes = [(key, sites)]."""
         pc = self.projector_calculator
         device = ipeps[plaquettes[0][1][0]]['A'].device
-        if device.type != "cuda":
-            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        ops.require_cuda_device(device)
         streams = self._side_streams(device)
         omegas = [pc.draw_omega(ipeps, sites, k) for _, sites in plaquettes]     # reference order of the RNG draws
         main = torch.cuda.current_stream(device)
         for st in streams:
             if st is not None:
                 st.wait_stream(main)
-        pend = [pc.begin(ipeps, sites, k, stream=streams[i % len(streams)], omega=omegas[i])
-                for i, (_, sites) in enumerate(plaquettes)]
-        out = {}
-        for (key, _), pd in zip(plaquettes, pend):
-            out[key] = pc.finish(pd)
+        out, retired = {}, []
+        for n, _, res in self._pipeline(ipeps, [(sites, k) for _, sites in plaquettes], omegas, streams, retired):
+            out[plaquettes[n][0]] = res
         for st in streams:
             if st is not None:
                 main.wait_stream(st)
-        del pend                     # Q tensors are released only after the main stream is ordered behind the side streams
+        del retired                  # per-task tensors are released only after the main stream is ordered behind the side streams
         return {key: v[0] for key, v in out.items()}, {key: v[1] for key, v in out.items()}
 
     # ---- task view of the moves -----------------------------------------------------------------------------------
@@ -364,48 +436,44 @@ class DirectionalMover:
         # may run -- on their own stream -- while the projectors of the following moves are still being computed
         pc = self.projector_calculator
         device = ipeps[tasks[0]["s1"]]['A'].device
-        if device.type != "cuda":
-            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
-        bulk, streams = self.phase_streams(device, len(tasks))
+        ops.require_cuda_device(device)
+        bulk, streams = self.phase_streams(device, min(len(tasks), self.inflight))
         omegas = [pc.draw_omega(ipeps, t["plaq"], t["k"]) for t in tasks]      # reference order of the RNG draws
         main = torch.cuda.current_stream(device)
         for st in streams + [bulk]:
             st.wait_stream(main)
-        pend = [pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n], bulk=bulk)
-                for n, t in enumerate(tasks)]
+        retired = []
+        pipe = self._pipeline(ipeps, [(t["plaq"], t["k"]) for t in tasks], omegas, streams, retired, bulk)
         p1, p2 = {}, {}
-        n0 = 0
         for g in groups:
-            pend_g = pend[n0:n0 + len(g)]
-            n0 += len(g)
             # the absorptions of a move read its source line and write the neighbouring line; when the two do not share a site
             # (every cell with at least two columns / rows) they can be issued piecewise, in any order
             piecewise = self.split_edge and {t["s1"] for t in g}.isdisjoint({t["s2"] for t in g})
             if piecewise:
-                self._finish_and_absorb_piecewise(ipeps, g, pend_g, p1, p2, bulk)
+                self._finish_and_absorb_piecewise(ipeps, g, pipe, p1, p2, bulk)
                 continue
-            for t, pd in zip(g, pend_g):
-                p1[(t["k"], t["key"])], p2[(t["k"], t["key"])] = pc.finish(pd)
+            for t in g:
+                _, pd, (p1[(t["k"], t["key"])], p2[(t["k"], t["key"])]) = next(pipe)
                 if pd.get("ready") is not None:
                     bulk.wait_event(pd["ready"])
             with torch.cuda.stream(bulk):          # outputs and scratch come from this stream's pool
                 for t in g:
                     self._absorb_task(ipeps, t, p1, p2)
+        pipe.close()
         for st in streams + [bulk]:
             main.wait_stream(st)
-        del pend
+        del retired                  # per-task tensors are released only after the main stream is ordered behind the side streams
 
-    def _finish_and_absorb_piecewise(self, ipeps, g, pend_g, p1, p2, bulk):
+    def _finish_and_absorb_piecewise(self, ipeps, g, pipe, p1, p2, bulk):
         """renormalize_boundary (directional_mover.py:293-303) of one move, issued on the bulk stream as soon as its inputs exist:
         the projector pair of task n is all that corner 1 of task n, corner 2 of its neighbour and the first stage of the
         neighbour's edge absorption need (directional_mover.py:295, 299, 301-303: proj1[i], proj2[j], proj1[j]); only the last
         GEMM of every edge absorption (proj2[i]) waits for the task's own chain.  After the last chain of a move, 2 x 4 ms of
         absorption work are left instead of 2 x 13.5 ms.  Same kernels in the same per-tensor order: bit-identical results."""
-        pc = self.projector_calculator
         t3 = {}
-        for t, pd in zip(g, pend_g):
+        for t in g:
             k, key = t["k"], t["key"]
-            p1[(k, key)], p2[(k, key)] = pc.finish(pd)
+            _, pd, (p1[(k, key)], p2[(k, key)]) = next(pipe)
             if pd.get("ready") is not None:
                 bulk.wait_event(pd["ready"])
             with torch.cuda.stream(bulk):          # outputs and scratch come from this stream's pool
@@ -436,25 +504,54 @@ class DirectionalMover:
         """Single-process counterpart of up_down_move_dist (directional_mover.py:228-271)."""
         self.move_pair(ipeps, [(1, y1), (3, y2)])
 
+    # ---- the moves `ipeps.evolve` issues after every bond update (acetn/evolution/fast_full_update.py:72-129) -----------------------
+    def absorb_bond(self, ipeps, bond):
+        """FastFullUpdater.absorb_bond (fast_full_update.py:72-99): the two opposite moves that absorb the updated bond, in the
+        reference's order (so the Omega draws keep their sequence); with half-system projectors they touch disjoint boundary
+        tensors and are run as one phase."""
+        s1, s2, k = bond
+        moves = {0: [(2, s1[0]), (0, s2[0])], 1: [(3, s1[1]), (1, s2[1])],
+                 2: [(0, s1[0]), (2, s2[0])], 3: [(1, s1[1]), (3, s2[1])]}[k]
+        pc = self.projector_calculator
+        if pc.projectors == "half-system" and os.environ.get("ACETN_B200_PAIR_MOVES", "1") != "0":
+            self.move_pair(ipeps, moves)
+            return
+        do = {0: self.left_move, 1: self.up_move, 2: self.right_move, 3: self.down_move}
+        for kk, line in moves:
+            do[kk](ipeps, line)
+
+    def _sharded_ctmrg(self, ipeps):
+        if self._sharded is None or self._sharded.ipeps is not ipeps:
+            from .distributed import B200Compute, ShardedCtmrg
+            self._sharded = ShardedCtmrg(ipeps, self._config, ipeps.rank, ipeps.world_size, compute=B200Compute(self._config, mover=self))
+        return self._sharded
+
+    def left_right_move_dist(self, ipeps, x1, x2):
+        """directional_mover.py:183-226 : left move on column x1 and right move on column x2 as one site-sharded phase."""
+        self._sharded_ctmrg(ipeps).phase([(0, x1), (2, x2)])
+
+    def up_down_move_dist(self, ipeps, y1, y2):
+        """directional_mover.py:228-271 : up move on row y1 and down move on row y2 as one site-sharded phase."""
+        self._sharded_ctmrg(ipeps).phase([(1, y1), (3, y2)])
+
     def _projectors_of_tasks(self, ipeps, tasks):
         pc = self.projector_calculator
         device = ipeps[tasks[0]["s1"]]['A'].device
-        if device.type != "cuda":
-            raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
+        ops.require_cuda_device(device)
         streams = self._side_streams(device)
         omegas = [pc.draw_omega(ipeps, t["plaq"], t["k"]) for t in tasks]      # reference order of the RNG draws
         main = torch.cuda.current_stream(device)
         for st in streams:
             if st is not None:
                 st.wait_stream(main)
-        pend = [pc.begin(ipeps, t["plaq"], t["k"], stream=streams[n % len(streams)], omega=omegas[n]) for n, t in enumerate(tasks)]
-        p1, p2 = {}, {}
-        for t, pd in zip(tasks, pend):
-            p1[(t["k"], t["key"])], p2[(t["k"], t["key"])] = pc.finish(pd)
+        p1, p2, retired = {}, {}, []
+        for n, _, res in self._pipeline(ipeps, [(t["plaq"], t["k"]) for t in tasks], omegas, streams, retired):
+            t = tasks[n]
+            p1[(t["k"], t["key"])], p2[(t["k"], t["key"])] = res
         for st in streams:
             if st is not None:
                 main.wait_stream(st)
-        del pend
+        del retired
         return p1, p2
 
     # ---- the four moves (directional_mover.py:23-97) -----------------------------------------------------------

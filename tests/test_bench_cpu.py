@@ -1,4 +1,5 @@
-"""CPU tests of bench.py's contract: the reference arm (`--impl reference`, the oracle port of the reference's CPU torch path)
+"""CPU tests of bench.py's contract: the reference arm (`--impl reference`: the unmodified reference package from oracle/_ref
+on the host cores, or the oracle port when it is absent)
 prints exactly one JSON line with the keys the driver reads, uses all host cores even when the launcher exported
 OMP_NUM_THREADS=1 (torchrun does), and non-zero ranks exit without work; the product arm refuses to run without a GPU."""
 import json
@@ -29,7 +30,9 @@ def test_reference_arm_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import vendor_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if vendor_ref.import_path() else "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["value"] == pytest.approx(1e3 / (16.0 * d["ms_per_step"]))      # a step is one site-move, a value-unit sweep is 16
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     assert d["cpu_baseline"]["cores"] == ncpu          # not the launcher's OMP_NUM_THREADS=1
 

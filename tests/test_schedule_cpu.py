@@ -236,3 +236,30 @@ def test_row_sharded_projector_gloo_world2(kind):
         assert ds < 1e-10, ds
         assert dpi < 1e-7, dpi
     assert ret[0][1:] == ret[1][1:]          # both ranks hold identical results
+
+
+@pytest.mark.parametrize("inflight", [1, 2])
+def test_inflight_window_does_not_change_results(inflight, monkeypatch):
+    """The bounded in-flight window of the phase scheduler (DirectionalMover._pipeline: at most W tasks hold their quarter
+    tensors; task n + W re-uses the slot of task n) must give the tensors of the unbounded schedule bit for bit -- host
+    logic, checked with the CPU stand-ins of the C-ABI wrappers on a 3x2 cell (6 tasks per up/down phase)."""
+    from acetn_b200.ipeps import CTMRGConfig, Ipeps
+    from acetn_b200.renormalization import DirectionalMover, ctmrg
+    from tests.cpu_emulation import emulated
+
+    def run(w):
+        monkeypatch.setenv("ACETN_B200_INFLIGHT", str(w))
+        cell = orc.random_cell(3, 2, 2, 6, 2, seed=5)
+        torch.manual_seed(21)
+        with emulated():
+            ip = Ipeps.from_plain(cell, CTMRGConfig(steps=2), device="cpu")
+            mover = DirectionalMover(ip.ctmrg_config)
+            assert mover.inflight == w
+            ctmrg(ip, ip.ctmrg_config, mover)
+            assert len(mover._slots) == min(w, 6)
+        return ip
+
+    a, b = run(16), run(inflight)
+    for s in a.site_list:
+        for k in range(4):
+            assert torch.equal(a[s]['C'][k], b[s]['C'][k]) and torch.equal(a[s]['E'][k], b[s]['E'][k])
