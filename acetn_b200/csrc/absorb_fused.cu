@@ -302,11 +302,7 @@ template <int D, int d>
 int launch_generic(const FusedParams& p, cudaStream_t s) {
     using C = FusedCfg<D, d>;
     static_assert(C::SMEM <= 227 * 1024, "fused double-layer: shared memory budget exceeded");
-    static bool configured = false;
-    if (!configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(double_layer_fused_generic_kernel<D, d>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
-    }
+    AB_ENSURE_SMEM((double_layer_fused_generic_kernel<D, d>), C::SMEM);
     const int64_t ngroups = (p.n0 * p.n1 + C::NB - 1) / C::NB;
     int grid = device_sm_count();
     if (ngroups < grid) grid = (int)ngroups;
@@ -351,11 +347,7 @@ int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t i
     AB_REQUIRE((((uintptr_t)X) & 15) == 0 && (in_s0 % 2) == 0 && (in_s1 % 2) == 0 && (in_es[0] % 2) == 0 && (in_es[1] % 2) == 0 &&
                    (in_es[2] % 2) == 0,
                "double_layer_fused: input block addressing must be 16-byte aligned");
-    static bool configured = false;
-    if (!configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(double_layer_fused_d8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM));
-        configured = true;
-    }
+    AB_ENSURE_SMEM(double_layer_fused_d8_kernel, FUSED_SMEM);
     int64_t nblk = n0 * n1;
     // one CTA per SM is resident at a time; `waves` CTAs per SM in the grid (each stages the site tensor once for >= 64 blocks)
     // bound the time a higher-priority stream waits for an SM (the rSVD chains of other site tasks, renormalization.py)

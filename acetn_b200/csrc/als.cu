@@ -227,11 +227,7 @@ int als_solve_launch(double* a1r, double* a2r, const double* n12g, const double*
     p.chol_in_smem = chol_bytes <= 200 * 1024 ? 1 : 0;
     size_t smem = p.chol_in_smem ? (chol_bytes > cost_bytes ? chol_bytes : cost_bytes) : cost_bytes;
     AB_REQUIRE(smem <= 220 * 1024, "als_solve: nD^2 pD^2 too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(als_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    AB_ENSURE_SMEM(als_kernel, smem);
     AB_CHECK_CUDA(cudaMemsetAsync(info, 0, 2 * sizeof(int), s));
     int grid = 32;
     int cap = device_sm_count();

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -112,6 +113,21 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 
 int device_sm_count();
 void note_launch(int n);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the "already configured" state of a kernel is kept per
+// device (the host shim initialises the library for every device index it meets) and is safe to race on from several host threads
+// (setting the attribute twice is harmless).  One SmemConfig per kernel instantiation, as a function-local static.
+constexpr int AB_MAX_DEVICES = 64;
+struct SmemConfig {
+    std::atomic<size_t> bytes[AB_MAX_DEVICES];
+    SmemConfig() { for (auto& b : bytes) b.store(0, std::memory_order_relaxed); }
+};
+int ensure_dynamic_smem(const void* kernel, SmemConfig& cfg, size_t bytes);
+#define AB_ENSURE_SMEM(kern, bytes)                                                              \
+    do {                                                                                         \
+        static ab200::SmemConfig _cfg;                                                           \
+        AB_TRY(ab200::ensure_dynamic_smem((const void*)(kern), _cfg, (size_t)(bytes)));          \
+    } while (0)
 #define AB_LAUNCHED()                                   \
     do {                                               \
         ab200::note_launch(1);                         \

@@ -435,11 +435,7 @@ int launch_cfg(const GemmKernelParams& kp, cudaStream_t stream) {
     using L = SmemLayout<BM, BN, A_MC, B_KC, BK>;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_KC, BK>;
-    static bool configured = false;
-    if (!configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        configured = true;
-    }
+    AB_ENSURE_SMEM(kern, L::BYTES);
     GemmKernelParams k2 = kp;
     int tiles_m = (kp.M + BM - 1) / BM;
     k2.tiles_mn = tiles_m * kp.tiles_n;

@@ -791,11 +791,7 @@ int i8_gemm_launch(const int8_t* Ares, int64_t rows, int64_t cols, int64_t ld, b
         AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
         const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
         AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
-        static size_t smem_set = 0;
-        if (smem_bytes > smem_set) {
-            AB_CHECK_CUDA(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-            smem_set = smem_bytes;
-        }
+        AB_ENSURE_SMEM(i8_gemm_kernel, smem_bytes);
         int grid = I8_NMOD * p.mtiles;
         if (grid > sms) grid = sms;
         i8_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, p);

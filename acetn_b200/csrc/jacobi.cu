@@ -242,11 +242,7 @@ int jacobi_svd_launch(const double* R, int q, double* S, double* Wt, double* Jt,
     jacobi_init_kernel<<<148, 256, 0, s>>>(X, J, R, q, g.n, g.ld);
     AB_LAUNCHED();
     {
-        static size_t configured = 0;
-        if (g.smem > configured) {
-            AB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-            configured = g.smem;
-        }
+        AB_ENSURE_SMEM(jacobi_block_kernel, g.smem);
         JacobiParams p;
         p.X = X; p.J = J; p.n = g.n; p.ld = g.ld; p.ncols = q; p.br = g.br; p.nb = g.nb; p.max_sweeps = max_sweeps;
         p.tol = 2.3e-16 * sqrt((double)(q > 64 ? q : 64)); p.conv = conv; p.info = info;

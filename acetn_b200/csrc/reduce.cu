@@ -24,14 +24,26 @@ long long launch_count() { return g_launch_counter.load(); }
 void reset_launch_count() { g_launch_counter.store(0); }
 
 int device_sm_count() {
-    static int sms = 0;
+    static std::atomic<int> cache[AB_MAX_DEVICES];          // per device (zero-initialised); benign race: every writer stores the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= AB_MAX_DEVICES) dev = 0;
+    int sms = cache[dev].load(std::memory_order_relaxed);
     if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev].store(sms, std::memory_order_relaxed);
     }
     return sms;
+}
+
+int ensure_dynamic_smem(const void* kernel, SmemConfig& cfg, size_t bytes) {
+    int dev = 0;
+    AB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= AB_MAX_DEVICES) { set_error("device index %d out of range", dev); return ERR_INVALID; }
+    if (cfg.bytes[dev].load(std::memory_order_acquire) >= bytes) return OK;
+    AB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    size_t cur = cfg.bytes[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !cfg.bytes[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+    return OK;
 }
 
 constexpr int RED_BLOCKS = 148 * 4;

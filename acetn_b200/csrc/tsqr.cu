@@ -235,11 +235,7 @@ size_t tsqr_scratch_doubles(int64_t m) {
 
 // orthonormalise one panel P (m x b, leading dimension ld) in place
 int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, const int* run_flag, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(tsqr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
-        configured = true;
-    }
+    AB_ENSURE_SMEM(tsqr_apply_kernel, APPLY_SMEM);
     Levels L = plan_levels(m, b);
     double* mat[9]; int64_t lds[9]; double* rst[8]; double* tau[8];
     mat[0] = P; lds[0] = ld;

@@ -63,10 +63,10 @@ def sv(t, rows):
     return torch.linalg.svdvals(t.reshape(rows, -1))
 
 
-def run_left_move(cell_gpu, engine):
-    """Oracle (torch on the GPU) and the B200 path on the same state and Omega -> everything the comparisons need."""
+def oracle_left_move(cell_gpu, tape):
+    """The oracle's left move of column 0 on the GPU -> (state after the move, spectra, proj1, proj2)."""
     cfg = orc.CtmrgConfig()
-    tape, rec = DeviceTape(), {}
+    rec = {}
     ref = cell_gpu.clone()
     tasks = orc.move_tasks(ref, 0, 0)
     rp1, rp2 = {}, {}
@@ -74,11 +74,15 @@ def run_left_move(cell_gpu, engine):
         rp1[key], rp2[key] = orc.half_system_projectors(ref, plaq, 0, cfg, tape, rec)
     for key, plaq, s1, s2, i, j in tasks:
         orc.renormalize_boundary(ref, rp1, rp2, s1, s2, i, j, 0)
+    return ref, rec["spectra"], rp1, rp2
+
+
+def b200_left_move(cell_gpu, engine, tape):
     ip = Ipeps.from_plain(cell_gpu, CTMRGConfig(thin_engine=engine), device=DEV)
     mover = DirectionalMover(ip.ctmrg_config)
     mover.projector_calculator.thin_engine = engine
     mover.projector_calculator.spectra = []
-    replay = orc.OmegaTape(tape.tape)
+    replay = orc.OmegaTape(tape)
     linalg.set_omega_source(replay)
     try:
         gp1, gp2 = mover._projectors_of_tasks(ip, mover.move_tasks(ip, 0, 0))
@@ -89,36 +93,60 @@ def run_left_move(cell_gpu, engine):
     finally:
         linalg.set_omega_source(None)
     torch.cuda.synchronize()
-    return ref, rec["spectra"], rp1, rp2, ip, spectra, gp1, gp2
+    got = orc.Cell(2, 2, ip.dims, {s: orc.Site(ip[s]['A'], list(ip[s]['C']), list(ip[s]['E'])) for s in ip.site_list})
+    return got, spectra, {k[1]: v for k, v in gp1.items()}, {k[1]: v for k, v in gp2.items()}
+
+
+def run_left_move(cell_gpu, engine):
+    """Oracle (torch on the GPU) and the B200 path on the same state and Omega."""
+    tape = DeviceTape()
+    ref = oracle_left_move(cell_gpu, tape)
+    got = b200_left_move(cell_gpu, engine, tape.tape)
+    return ref, got, tape.tape
+
+
+def deviations(a, b, chi):
+    """Gauge-invariant deviations of move result `a` = (state, spectra, proj1, proj2) from `b`."""
+    sa, sb = a[1], b[1]
+    out = {"spectra": max(float((x.to(DEV) - y.to(DEV))[:chi].abs().max()) for x, y in zip(sa, sb)),
+           "pi": max(pi_rel_diff(a[2][k], a[3][k], b[2][k], b[3][k]) for k in b[2])}
+    worst = 0.0
+    for y in range(2):
+        for ta, tb in ((a[0][(1, y)].C[3], b[0][(1, y)].C[3]), (a[0][(1, y)].C[0], b[0][(1, y)].C[0]), (a[0][(1, y)].E[3], b[0][(1, y)].E[3])):
+            assert ta.shape == tb.shape
+            va, vb = sv(ta, ta.shape[0]), sv(tb, tb.shape[0])
+            worst = max(worst, float((va - vb).abs().max() / vb[0]))
+    out["absorbed_sv"] = worst
+    r0, r1 = orc.site_rdm(b[0], (1, 0)), orc.site_rdm(a[0], (1, 0))
+    out["site_rdm"] = float((r0 / r0.trace() - r1 / r1.trace()).abs().max())
+    return out
 
 
 @pytest.mark.parametrize("D,chi,d,engine", [(8, 256, 2, "i8"), (8, 256, 2, "dmma"), (6, 144, 2, "i8"), (6, 144, 2, "dmma"),
                                             (7, 196, 4, "i8"), (7, 196, 4, "dmma")])
 def test_headline_size_left_move_vs_oracle_on_gpu(D, chi, d, engine):
+    """Tolerances: truncated spectra 1e-10 of s0 (north star), unconditionally.  The other three quantities involve the projectors
+    themselves, i.e. singular VECTORS scaled by s^-1/2: on synthetic random tensors the spectrum is dense at the cut (gap
+    s_chi - s_chi+1 ~ 1e-5 s0, s_chi ~ 1e-3 s0), so rounding-level differences are amplified by ~ s0 / (gap sqrt(s_chi)); how much
+    is MEASURED on the reference itself: the oracle re-run with a mathematically equivalent QR basis (tests/util.rotated_qr).  They
+    must stay within max(1e-9, 3 x that envelope)."""
+    from tests.util import rotated_qr
     cell = cell_to(orc.random_cell(2, 2, D, chi, d, seed=0), DEV)
     torch.manual_seed(17)
-    ref, s_ref, rp1, rp2, ip, s_got, gp1, gp2 = run_left_move(cell, engine)
+    ref, got, tape = run_left_move(cell, engine)
     if engine == "i8":
         assert ops.i8_supported(chi * D * D, chi * D * D, chi + 2)
-    # (i) truncated spectra of both projectors of the move
-    assert len(s_ref) == len(s_got) == 2
-    for a, b in zip(s_ref, s_got):
-        assert float((a.to(DEV) - b.to(DEV))[:chi].abs().max()) < 1e-10
-    # (ii) the gauge-invariant projector product Pi = P2 P1^T
-    for key in rp1:
-        assert gp1[(0, key)].shape == rp1[key].shape and gp2[(0, key)].shape == rp2[key].shape
-        assert pi_rel_diff(gp1[(0, key)], gp2[(0, key)], rp1[key], rp2[key]) < 1e-9
-    # (iii) the absorbed tensors of column 1 through their singular values (invariant under the sign / rotation gauge of U, V)
-    for y in range(2):
-        a, b = ref[(1, y)], ip[(1, y)]
-        for ta, tb in ((a.C[3], b['C'][3]), (a.C[0], b['C'][0]), (a.E[3], b['E'][3])):
-            assert ta.shape == tb.shape
-            sa, sb = sv(ta, ta.shape[0]), sv(tb, tb.shape[0])
-            assert float((sa - sb).abs().max() / sa[0]) < 1e-9
-    # (iv) site RDM of an updated site (uses the new C[3], C[0], E[3] together with the untouched rest)
-    got = orc.Cell(2, 2, ip.dims, {s: orc.Site(ip[s]['A'], list(ip[s]['C']), list(ip[s]['E'])) for s in ip.site_list})
-    r0, r1 = orc.site_rdm(ref, (1, 0)), orc.site_rdm(got, (1, 0))
-    assert float((r0 / r0.trace() - r1 / r1.trace()).abs().max()) < 1e-9
+    assert len(ref[1]) == len(got[1]) == 2
+    for key in ref[2]:
+        assert got[2][key].shape == ref[2][key].shape and got[3][key].shape == ref[3][key].shape
+    dev = deviations(got, ref, chi)
+    with rotated_qr(seed=2):
+        ref_rot = oracle_left_move(cell, orc.OmegaTape(tape))
+    env = deviations(ref_rot, ref, chi)
+    print(f"D={D} chi={chi} d={d} {engine}: b200-vs-oracle {dev}   oracle-vs-oracle(rotated QR) {env}")
+    assert dev["spectra"] < 1e-10
+    for k in ("pi", "absorbed_sv", "site_rdm"):
+        assert dev[k] <= max(1e-9, 3.0 * env[k]), (k, dev[k], env[k])
 
 
 def graded_cell(D, chi, d, decades, seed):
@@ -136,26 +164,25 @@ def graded_cell(D, chi, d, decades, seed):
 @pytest.mark.parametrize("D,chi", [(8, 64), (6, 144)])
 def test_k7_on_graded_boundary_vs_k1_and_oracle(D, chi):
     """m = chi D^2 >= 4096 (K7 active under 'auto'), boundary graded over 10 decades: K7, K1 and torch must agree on the
-    truncated spectra (1e-10 of s0), on Pi and on the absorbed tensors."""
+    truncated spectra (1e-10 of s0), on the truncated rank, and -- within the reference's own envelope -- on Pi and the
+    absorbed tensors."""
+    from tests.util import rotated_qr
     cell = cell_to(graded_cell(D, chi, 2, 10.0, seed=3), DEV)
     assert chi * D * D >= ProjectorCalculator.I8_MIN_DIM
-    out = {}
+    torch.manual_seed(23)
+    tape = DeviceTape()
+    ref = oracle_left_move(cell, tape)
+    with rotated_qr(seed=2):
+        env = deviations(oracle_left_move(cell, orc.OmegaTape(tape.tape)), ref, chi)
     for engine in ("i8", "dmma"):
-        torch.manual_seed(23)
-        out[engine] = run_left_move(cell, engine)
-    ref, s_ref, rp1, rp2 = out["i8"][:4]
-    for engine in ("i8", "dmma"):
-        _, _, _, _, ip, s_got, gp1, gp2 = out[engine]
-        for a, b in zip(s_ref, s_got):
-            assert a.shape == b.shape
-            assert float((a.to(DEV) - b.to(DEV))[:chi].abs().max()) < 1e-10, engine
-        for key in rp1:
-            assert gp1[(0, key)].shape == rp1[key].shape, engine      # same truncated rank chi'
-            assert pi_rel_diff(gp1[(0, key)], gp2[(0, key)], rp1[key], rp2[key]) < 1e-8, engine
-        for y in range(2):
-            for ta, tb in ((ref[(1, y)].C[3], ip[(1, y)]['C'][3]), (ref[(1, y)].E[3], ip[(1, y)]['E'][3])):
-                sa, sb = sv(ta, ta.shape[0]), sv(tb, tb.shape[0])
-                assert float((sa - sb).abs().max() / sa[0]) < 1e-9, engine
+        got = b200_left_move(cell, engine, tape.tape)
+        for key in ref[2]:
+            assert got[2][key].shape == ref[2][key].shape, engine      # same truncated rank chi'
+        dev = deviations(got, ref, chi)
+        print(f"graded D={D} chi={chi} {engine}: b200-vs-oracle {dev}   oracle-vs-oracle(rotated QR) {env}")
+        assert dev["spectra"] < 1e-10, engine
+        for k in ("pi", "absorbed_sv", "site_rdm"):
+            assert dev[k] <= max(1e-9, 3.0 * env[k]), (engine, k, dev[k], env[k])
 
 
 @pytest.mark.parametrize("kind", ["spectrum", "rowcol"])

@@ -56,7 +56,7 @@ class rotated_qr:
         def qr(Y, mode="reduced"):
             Q, R = real(Y, mode=mode)
             g = torch.Generator().manual_seed(seed * 1000003 + Q.shape[0] * 7 + Q.shape[1])
-            G = real(torch.randn(Q.shape[1], Q.shape[1], dtype=Q.dtype, generator=g)).Q
+            G = real(torch.randn(Q.shape[1], Q.shape[1], dtype=Q.dtype, generator=g)).Q.to(Q.device)
             return QR(Q @ G, G.mH @ R)
         torch.linalg.qr = qr
         return self
