@@ -64,6 +64,12 @@ SIGNATURES = {
     "acetn_b200_fp64_peak_probe": (c_dbl, [c_vp, c_int, c_vp]),
     "acetn_b200_als_workspace_bytes": (c_sz, [c_i64] * 3),
     "acetn_b200_als_solve": (c_int, [c_vp] * 5 + [c_i64] * 4 + [c_dbl, c_dbl, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_site_rdm_workspace_bytes": (c_sz, [P_i64, c_i64, c_i64]),
+    "acetn_b200_site_rdm": (c_int, [c_vp] * 9 + [P_i64, P_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_bond_rdm_workspace_bytes": (c_sz, [P_i64, c_i64, c_i64]),
+    "acetn_b200_bond_rdm": (c_int, [c_vp] * 6 + [P_i64] + [c_vp] * 6 + [P_i64, P_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_norm_tensor_workspace_bytes": (c_sz, [P_i64, c_i64, c_i64]),
+    "acetn_b200_norm_tensor": (c_int, [c_vp] * 12 + [P_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_permute": (c_int, [c_vp, c_vp, c_int, P_i64, P_i64, c_vp]),
     "acetn_b200_absmax": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "acetn_b200_frob_normalize": (c_int, [c_vp, c_i64, c_vp, c_sz, c_vp]),

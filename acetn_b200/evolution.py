@@ -2,7 +2,8 @@
 solver (acetn/evolution/als_solver.py) and -- SURVEY.md 8f-1 -- the callers around them in one bond update: QR split
 (tensor_update.py:53-75), positive_approx / gauge_fix (full_update.py:262-343), finalize_reduced_tensors (:121-161).
 
-Everything dense runs on the library's own kernels (no cuSOLVER): contractions = gather + batched K1 DGEMM (`ops.contract`),
+Everything dense runs on the library's own kernels (no cuSOLVER): the norm tensor behind acetn_b200_norm_tensor, the small
+contractions = gather + batched K1 DGEMM (`ops.contract`),
 thin QR = K4 Householder TSQR + one K1 product for R, symmetric eigen-decomposition / SVD / pseudo-inverse of the small
 matrices (<= 256 x 256) = K5 one-sided Jacobi, ALS loop = K6.  `ALSSolver` keeps the reference's constructor/solve() shape so
 it can replace `ALSSolver(n12, a12g, ar_shape, config).solve()` when `config.backend == "b200"` (als_solver.py:48-51);
@@ -13,112 +14,19 @@ from . import ops
 from .ops import contract
 
 
-import os as _os
-
-_SMALL_K_TILE = int(_os.environ.get("ACETN_B200_ENV_TILE", "0"))      # K1 tile of the K = D^2 steps (0 = planner's choice)
-
-
-def _ix(*triples):
-    """27 ints of ops.gemm_ex: {div, s_hi, s_lo} for A(m, k, batch), B(k, n, batch), C(m, n, batch); a plain int is a stride."""
-    out = []
-    for t in triples:
-        out += [0, 0, t] if isinstance(t, int) else list(t)
-    return out
-
-
-def env_front(cA, eA, eB):
-    """t[(c,p,P),(e,q,Q)] = sum_{a,b} cA[a,b] eA[b,c,p,P] eB[e,a,q,Q]: the boundary part of a bond-environment half (full_update.py
-    :205-206 / :220-221, rdm.py:95-96 / :100-101), shared by everything that is contracted with site tensors afterwards."""
-    x0, x1 = cA.shape
-    xc, D = eA.shape[1], eA.shape[2]
-    xe = eB.shape[0]
-    D2 = D * D
-    t1 = ops.matmul(cA.contiguous(), eA.contiguous().reshape(x1, xc * D2))            # t1[a,(c,p,P)]
-    m, n = xc * D2, xe * D2
-    t = torch.empty(m, n, dtype=cA.dtype, device=cA.device)
-    ops.gemm_ex(m, n, x0, 1, t1, eB.contiguous(), t, _ix(1, m, 0, D2, (D2, x0 * D2, 1), 0, n, 1, 0))
-    return t, (xc, xe, D)
-
-
-def env_back(t, dims, A5, bra, ket, Yb, yk, left):
-    """out[f, n-leg chi, Yb, yk] from t = env_front(...), the closing boundary A5[f][k-leg chi][(d,D)] and the site factors as
-    plain matrices:  bra[(P,Q)][Nb], ket[(p,q)][(d,yk)]  with  Nb enumerated (D,Yb) (right half) or (Yb,D) (left half).
-        right: k-leg = c (first chi leg of t), n-leg = e        left: k-leg = e, n-leg = c
-    Every leg permutation of the reference's einsum chain is folded into the two-level index descriptors of K1, so none of the
-    2 - 8 GiB intermediates is re-laid out in HBM (the generic gather + GEMM form spent 42 % of its time in gathers)."""
-    xc, xe, D = dims
-    dev, dt = t.device, t.dtype
-    D2 = D * D
-    n = xe * D2
-    Nb, Nk = D * Yb, D * yk
-    # 3. t2[c,p,e,q,Nb] = sum_{P,Q} t[c,p,P,e,q,Q] bra[(P,Q),Nb]
-    M3 = xc * D * xe * D
-    t2 = torch.empty(M3, Nb, dtype=dt, device=dev)
-    a_m = (xe * D, D * n, D)               # hi = (c,p): stride D*n, lo = (e,q): stride D
-    a_k = (D, n, 1)                        # hi = P: stride n, lo = Q: stride 1
-    ops.gemm_ex(M3, Nb, D2, 1, t, bra, t2, _ix(a_m, a_k, 0, Nb, 1, 0, Nb, 1, 0), force_tile=_SMALL_K_TILE)
-    # 4. per (c,e): t3[Nb,(d,yk)] = sum_{p,q} t2[c,p,e,q,Nb] ket[(p,q),(d,yk)], written straight into the layout step 5 wants:
-    #    [k-leg chi][d][D][n-leg chi][Yb][yk]
-    kl, nl = (xc, xe) if not left else (xe, xc)
-    nn = Yb * yk
-    t3 = torch.empty(kl, D, D, nl, Yb, yk, dtype=dt, device=dev)
-    s_e4, s_c4 = D * Nb, D * xe * D * Nb                              # strides of e and c in t2[c,p,e,q,Nb]
-    a_b = (xe, s_c4, s_e4)                                            # batch = (c,e)
-    a_k4 = (D, xe * D * Nb, Nb)                                       # k = (p,q)
-    s_d, s_D, s_n, s_Y = D * nl * nn, nl * nn, nn, yk
-    if not left:
-        c_b = (xe, D * D * nl * nn, s_n)                              # c -> k leg, e -> n leg
-        c_m = (Yb, s_D, s_Y)                                          # m = (D,Yb)
-    else:
-        c_b = (xe, s_n, D * D * nl * nn)                              # c -> n leg, e -> k leg
-        c_m = (D, s_Y, s_D)                                           # m = (Yb,D)
-    c_n = (yk, s_d, 1)                                                # n = (d,yk): yk innermost => coalesced stores
-    ops.gemm_ex(Nb, Nk, D2, xc * xe, t2, ket, t3, _ix(1, a_k4, a_b, Nk, 1, 0, c_m, c_n, c_b), force_tile=_SMALL_K_TILE)
-    del t2
-    # 5. out[f,(n-leg chi, Yb, yk)] = sum_{k-leg chi, d, D} A5[f,(k-leg chi, d, D)] t3[(k-leg chi, d, D), (...)]
-    xf = A5.shape[0]
-    out = ops.matmul(A5.reshape(xf, kl * D2), t3.reshape(kl * D2, nl * nn))
-    return out.reshape(xf, nl, Yb, yk)
-
-
-def closing_right(cB, eC):
-    """tmp_r2[a,f,d,D] = cB[a,b] eC[b,f,d,D] (full_update.py:207, rdm.py:97) as A5[f][a][(d,D)]."""
-    D2 = eC.shape[2] * eC.shape[3]
-    xf = eC.shape[1]
-    return ops.matmul(cB.contiguous(), eC.contiguous().reshape(cB.shape[1], xf * D2)).reshape(cB.shape[0], xf, D2).permute(1, 0, 2).contiguous()
-
-
-def closing_left(cB, eC):
-    """tmp_l2[b,f,d,D] = cB[a,b] eC[f,a,d,D] (full_update.py:222, rdm.py:102) as A5[f][b][(d,D)]."""
-    return contract("ab,fadD->fbdD", cB, eC).contiguous()
-
-
 def build_norm_tensor(ipeps, bond, a1q, a2q):
-    """full_update.py:163-227 : N12[y,x,Y,X]; bond = (s1, s2, k); a1q/a2q (D,D,D,nD).
-        right: n1[f,e,Y,y] = sum tmp_r2[a,f,d,D] ( ((c12 e12) e11) conj(a1q)[R,D,U,Y] a1q[r,d,u,y] )[a,e,D,Y,d,y]
-        left : n2[f,c,X,x] = sum tmp_l2[b,f,d,D] ( ((c21 e21) e24) conj(a2q)[D,L,U,X] a2q[d,l,u,x] )[c,b,X,D,x,d]"""
+    """full_update.py:163-227 : N12[y,x,Y,X]; bond = (s1, s2, k); a1q/a2q (D,D,D,nD).  One C-ABI call (acetn_b200_norm_tensor,
+    acetn_b200/csrc/environment.cu): every leg permutation of the reference's einsum chain is folded into K1's two-level index
+    descriptors, so the 2 / 4 / 8 GiB intermediates are written once in the layout the next GEMM reads."""
     s1, s2, k = bond
-    a, b = ipeps[s1], ipeps[s2]
-    c12, e12, e11 = a['C'][(k + 1) % 4], a['E'][(k + 1) % 4], a['E'][k % 4]
-    c13, e13 = a['C'][(k + 2) % 4], a['E'][(k + 2) % 4]
-    c21, e21, e24 = b['C'][k % 4], b['E'][k % 4], b['E'][(k + 3) % 4]
-    c24, e23 = b['C'][(k + 3) % 4], b['E'][(k + 2) % 4]
-    D, nD = a1q.shape[0], a1q.shape[3]
-    # the 64 KiB site factors as plain (k, n) matrices (conj is the identity: FP64 real)
-    q1 = a1q.permute(0, 2, 1, 3).contiguous().reshape(D * D, D * nD)                    # [(R,U)][(D,Y)] = [(r,u)][(d,y)]
-    t, dims = env_front(c12, e12, e11)
-    n1 = env_back(t, dims, closing_right(c13, e13), q1, q1, nD, nD, left=False)        # [f,e,Y,y]
-    del t
-    bra2 = a2q.permute(2, 1, 3, 0).contiguous().reshape(D * D, nD * D)                  # [(U,L)][(X,D)]
-    ket2 = a2q.permute(2, 1, 0, 3).contiguous().reshape(D * D, D * nD)                  # [(u,l)][(d,x)]
-    t, dims = env_front(c21, e21, e24)
-    n2 = env_back(t, dims, closing_left(c24, e23), bra2, ket2, nD, nD, left=True)      # [f,c,X,x]
-    del t
-    return contract("fcYy,fcXx->yxYX", n1, n2).contiguous()
+    return ops.norm_tensor(ipeps[s1], ipeps[s2], k, a1q, a2q)
 
 
 class ALSSolver:
-    """als_solver.py:6-82 with the iteration loop in libacetn_b200.so (one cooperative kernel, convergence on device)."""
+    """als_solver.py:6-82.  method "cholesky" (default): the whole iteration loop in libacetn_b200.so (K6, one cooperative
+    kernel, convergence test on the device).  method "pinv" (als_solver.py:226-228 = csrc/evolution/als_solve.cpp:47-50): the
+    reference's host-driven loop, every contraction / decomposition on the library's kernels (K1 contractions, K4 + K5
+    symmetric eigen-decomposition), one host read of the cost per iteration like the reference (als_solver.py:78-79)."""
 
     def __init__(self, n12, a12g, ar_shape, config):
         self.niter = config.als_niter
@@ -127,8 +35,8 @@ class ALSSolver:
         self.epsilon = config.als_epsilon
         self.n12, self.a12g, self.ar_shape = n12, a12g, ar_shape
         self.info = None
-        if self.method != "cholesky":
-            raise NotImplementedError("backend='b200': als_method must be 'cholesky'")
+        if self.method not in ("cholesky", "pinv"):
+            raise ValueError(f"Invalid als_method: {self.method} provided.")
 
     def initialize_tensors(self):
         """als_solver.py:112-146 (SVD of the (nD pD) x (nD pD) gate-tensor product on K5)."""
@@ -144,7 +52,51 @@ class ALSSolver:
 
     def solve(self):
         a1r, a2r, n12g = self.initialize_tensors()
+        if self.method == "pinv":
+            return self.solve_pinv(a1r, a2r, n12g)
         a1r, a2r, self.info = ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon)
+        return a1r, a2r
+
+    # ---- method "pinv" ------------------------------------------------------------------------------------------------
+    def solve_ar_pinv(self, R, S):
+        """als_solver.py:213-229, pinv branch: ar = pinv(R_sym, hermitian=True, rcond=epsilon) @ S."""
+        nD, bD, pD = S.shape
+        n = nD * bD
+        R = R.reshape(n, n)
+        R = (0.5 * (R + R.t())).contiguous()
+        w, V = eigh_sym(R)
+        keep = w.abs() > self.epsilon * w.abs().max()
+        winv = torch.where(keep, 1.0 / torch.where(keep, w, torch.ones_like(w)), torch.zeros_like(w))
+        y = ops.matmul(V, S.reshape(n, pD).contiguous(), transpose_a=True)          # V^T S
+        return ops.matmul(V, (y * winv[:, None]).contiguous()).reshape(nD, bD, pD)
+
+    def calculate_cost(self, a1r, a2r):
+        """als_solver.py:246-257."""
+        a12n = contract("yup,xuq->yxpq", a1r, a2r).contiguous()
+        d2 = contract("yxYX,yxpq->YXpq", self.n12, a12n)
+        d3 = contract("yxYX,yxpq->YXpq", self.n12, self.a12g)
+        return ((d2 - 2.0 * d3) * a12n).sum()
+
+    def solve_pinv(self, a1r, a2r, n12g):
+        """als_solver.py:55-82 with solve_ar's pinv branch."""
+        n12 = self.n12
+        d1 = abs(float(self.calculate_cost(a1r, a2r)))
+        it = 0
+        for i in range(self.niter):
+            it = i + 1
+            S = contract("YXpQ,XUQ->YUp", n12g, a2r).contiguous()
+            R = contract("yxYX,xuq->yYXuq", n12, a2r)
+            R = contract("yYXuQ,XUQ->YUyu", R.contiguous(), a2r).contiguous()
+            a1r = self.solve_ar_pinv(R, S)
+            S = contract("YXPq,YVP->XVq", n12g, a1r).contiguous()
+            R = contract("yxYX,yvp->xYXvp", n12, a1r)
+            R = contract("xYXvP,YVP->XVxv", R.contiguous(), a1r).contiguous()
+            a2r = self.solve_ar_pinv(R, S)
+            d2 = float(self.calculate_cost(a1r, a2r))       # the reference's one host read per iteration (als_solver.py:78-79)
+            if abs(d2 - d1) / abs(d1) < self.tol and i > 1:
+                break
+            d1 = d2
+        self.info = torch.tensor([it, 0], dtype=torch.int32)
         return a1r, a2r
 
 

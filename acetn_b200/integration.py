@@ -23,6 +23,7 @@ The reference's SiteTensor / TensorNetwork objects are used as they are: the B20
 `bond_permute`, `ipeps.nx/ny/dims` and writes list items in place exactly like directional_mover.py:295-303.
 """
 import functools
+from types import SimpleNamespace
 
 from . import _lib
 
@@ -85,7 +86,6 @@ def install(acetn_module=None):
     import acetn.evolution.als_solver as als_mod
     import acetn.evolution.full_update as fu_mod
     from . import evolution as b200_evo
-    from . import ops as b200_ops
     ref_norm = fu_mod.build_norm_tensor
 
     def build_norm_tensor(ipeps, bond, a1q, a2q):
@@ -98,11 +98,8 @@ def install(acetn_module=None):
 
     def solve(self):
         if self.backend == "b200":
-            if self.method != "cholesky":
-                raise NotImplementedError("backend='b200': als_method must be 'cholesky'")
-            a1r, a2r, n12g = self.initialize_tensors()
-            a1r, a2r, _ = b200_ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon)
-            return a1r, a2r
+            cfg = SimpleNamespace(als_niter=self.niter, als_tol=self.tol, als_method=self.method, als_epsilon=self.epsilon)
+            return b200_evo.ALSSolver(self.n12, self.a12g, tuple(self.ar_shape), cfg).solve()
         return ref_solve(self)
 
     als_mod.ALSSolver.solve = solve

@@ -391,6 +391,77 @@ def contract(spec, A, B):
     return C.permute([order.index(c) for c in out])
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# environment contractions behind the C ABI (acetn_b200/csrc/environment.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _chi2(*tensors):
+    out = []
+    for t in tensors:
+        out += [t.shape[0], t.shape[1]]
+    return out
+
+
+def site_rdm(C, E, A):
+    """RDM.build_site_rdm (rdm.py:35-67): C, E = the four corners / edges of the site, A = site['A'] (any strides) -> rho (d,d)."""
+    dev = _require_cuda(*C, *E, A)
+    C = [c.contiguous() for c in C]
+    E = [e.contiguous() for e in E]
+    D, d = A.shape[0], A.shape[4]
+    chi = _lib.i64_array(_chi2(*C, *E))
+    lib = _lib.load()
+    rho = torch.empty(d, d, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_site_rdm_workspace_bytes(chi, D, d))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_site_rdm(_p(C[0]), _p(C[1]), _p(C[2]), _p(C[3]), _p(E[0]), _p(E[1]), _p(E[2]), _p(E[3]), _p(A),
+                                     _lib.i64_array(A.stride()), chi, D, d, _p(rho), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "site_rdm")
+    return rho
+
+
+def _bond_boundary(a, b, k):
+    """The ten boundary tensors of the bond (s1, s2, k) in the argument order of acetn_b200_bond_rdm / _norm_tensor
+    (rdm.py:84-96, full_update.py:184-196); a, b = the two site-tensor objects."""
+    return [a['C'][(k + 1) % 4], a['E'][(k + 1) % 4], a['E'][k % 4], a['C'][(k + 2) % 4], a['E'][(k + 2) % 4],
+            b['C'][k % 4], b['E'][k % 4], b['E'][(k + 3) % 4], b['C'][(k + 3) % 4], b['E'][(k + 2) % 4]]
+
+
+def bond_rdm(site1, site2, k):
+    """RDM.build_bond_rdm (rdm.py:69-154) of the bond (s1, s2, k): site1 / site2 = the reference's (or acetn_b200's) SiteTensor
+    objects -> rho (d,d,d,d) [P,Q,p,q]."""
+    a1, a2 = site1.bond_permute(k), site2.bond_permute(k)
+    bt = [t.contiguous() for t in _bond_boundary(site1, site2, k)]
+    dev = _require_cuda(*bt, a1, a2)
+    D, d = a1.shape[0], a1.shape[4]
+    chi = _lib.i64_array(_chi2(*bt))
+    lib = _lib.load()
+    rho = torch.empty(d, d, d, d, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_bond_rdm_workspace_bytes(chi, D, d))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_bond_rdm(_p(bt[0]), _p(bt[1]), _p(bt[2]), _p(bt[3]), _p(bt[4]), _p(a1), _lib.i64_array(a1.stride()),
+                                     _p(bt[5]), _p(bt[6]), _p(bt[7]), _p(bt[8]), _p(bt[9]), _p(a2), _lib.i64_array(a2.stride()),
+                                     chi, D, d, _p(rho), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "bond_rdm")
+    return rho
+
+
+def norm_tensor(site1, site2, k, a1q, a2q):
+    """build_norm_tensor (full_update.py:163-227) of the bond (s1, s2, k) with the QR-reduced site factors a1q, a2q (D,D,D,nD)
+    -> N12 (nD,nD,nD,nD) [y,x,Y,X]."""
+    bt = [t.contiguous() for t in _bond_boundary(site1, site2, k)]
+    a1q, a2q = a1q.contiguous(), a2q.contiguous()
+    dev = _require_cuda(*bt, a1q, a2q)
+    D, nD = a1q.shape[0], a1q.shape[3]
+    chi = _lib.i64_array(_chi2(*bt))
+    lib = _lib.load()
+    n12 = torch.empty(nD, nD, nD, nD, dtype=torch.float64, device=dev)
+    ws = _ws(dev, lib.acetn_b200_norm_tensor_workspace_bytes(chi, D, nD))
+    with torch.cuda.device(dev):
+        st = lib.acetn_b200_norm_tensor(_p(bt[0]), _p(bt[1]), _p(bt[2]), _p(bt[3]), _p(bt[4]), _p(a1q), _p(bt[5]), _p(bt[6]), _p(bt[7]),
+                                        _p(bt[8]), _p(bt[9]), _p(a2q), chi, D, nD, _p(n12), _p(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "norm_tensor")
+    return n12
+
+
 def absmax(x, out):
     """out[0] = max(out[0], max|x|)  (out: 1-element device tensor, zero it first)."""
     dev = _require_cuda(x, out)

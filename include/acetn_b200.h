@@ -203,6 +203,33 @@ int acetn_b200_als_solve(double* a1r, double* a2r, const double* n12g, const dou
                          int64_t bD, int64_t pD, int64_t niter, double tol, double epsilon, int32_t* info, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* ---- environment contractions of `measure` and of the full update (SURVEY.md 8b minimum set; acetn_b200/csrc/environment.cu) --------
+ *   Every step is a K1 launch whose index descriptors absorb the leg permutations of the reference's einsum chain.
+ *   chi: the chi extents of the boundary tensors, 2 per tensor in ARGUMENT ORDER (chi legs may differ); the
+ *   entry points check that contracted legs agree.  Site-tensor arguments are strided views (5 element strides, legs l,u,r,d,p).
+ *
+ *   site_rdm : RDM.build_site_rdm, acetn/measurement/rdm.py:35-67.   c1..c4 = site.C[0..3], e1..e4 = site.E[0..3], A = site['A'];
+ *              chi = 16 extents (c1,c2,c3,c4,e1,e2,e3,e4);  rho out: (d,d) [bra P, ket p].
+ *   bond_rdm : RDM.build_bond_rdm + build_bond_rdm_core_blocked, rdm.py:69-154, for the bond (s1, s2, k):
+ *              c12 = s1.C[(k+1)%4], e12 = s1.E[(k+1)%4], e11 = s1.E[k], c13 = s1.C[(k+2)%4], e13 = s1.E[(k+2)%4], a1 = s1.bond_permute(k),
+ *              c21 = s2.C[k], e21 = s2.E[k], e24 = s2.E[(k+3)%4], c24 = s2.C[(k+3)%4], e23 = s2.E[(k+2)%4], a2 = s2.bond_permute(k);
+ *              chi = 20 extents (c12,e12,e11,c13,e13,c21,e21,e24,c24,e23);  rho out: (d,d,d,d) [P,Q,p,q].
+ *   norm_tensor : build_norm_tensor, acetn/evolution/full_update.py:163-227: the same ten boundary tensors with the QR-reduced site
+ *              factors a1q, a2q (D,D,D,nD) contiguous;  n12 out: (nD,nD,nD,nD) [y,x,Y,X]. */
+size_t acetn_b200_site_rdm_workspace_bytes(const int64_t* chi, int64_t D, int64_t d);
+int acetn_b200_site_rdm(const double* c1, const double* c2, const double* c3, const double* c4, const double* e1, const double* e2,
+                        const double* e3, const double* e4, const double* A, const int64_t* a_strides, const int64_t* chi, int64_t D,
+                        int64_t d, double* rho, void* ws, size_t ws_bytes, void* stream);
+size_t acetn_b200_bond_rdm_workspace_bytes(const int64_t* chi, int64_t D, int64_t d);
+int acetn_b200_bond_rdm(const double* c12, const double* e12, const double* e11, const double* c13, const double* e13, const double* a1,
+                        const int64_t* a1_strides, const double* c21, const double* e21, const double* e24, const double* c24,
+                        const double* e23, const double* a2, const int64_t* a2_strides, const int64_t* chi, int64_t D, int64_t d,
+                        double* rho, void* ws, size_t ws_bytes, void* stream);
+size_t acetn_b200_norm_tensor_workspace_bytes(const int64_t* chi, int64_t D, int64_t nD);
+int acetn_b200_norm_tensor(const double* c12, const double* e12, const double* e11, const double* c13, const double* e13, const double* a1q,
+                           const double* c21, const double* e21, const double* e24, const double* c24, const double* e23, const double* a2q,
+                           const int64_t* chi, int64_t D, int64_t nD, double* n12, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- generic pairwise contraction support (measure / norm-tensor paths: rdm.py:35-154, full_update.py:209-227): the
  *      transpose step of a transpose-transpose-GEMM-transpose contraction (what cuTENSOR's TTGT plan does in the
  *      reference's extension, csrc/linalg/contraction.h:263).  dst is contiguous row-major over dims[0..nd);

@@ -192,9 +192,27 @@ def i8_supported(rows, cols, q):
     return False
 
 
+def _plain_site(st):
+    return orc.Site(st['A'], list(st['C']), list(st['E']))
+
+
+def site_rdm(C, E, A):
+    return orc.site_rdm(orc.Cell(1, 1, {}, {(0, 0): orc.Site(A, list(C), list(E))}), (0, 0)).contiguous()
+
+
+def bond_rdm(site1, site2, k):
+    cell = orc.Cell(2, 1, {}, {(0, 0): _plain_site(site1), (1, 0): _plain_site(site2)})
+    return orc.bond_rdm(cell, ((0, 0), (1, 0), k)).contiguous()
+
+
+def norm_tensor(site1, site2, k, a1q, a2q):
+    cell = orc.Cell(2, 1, {}, {(0, 0): _plain_site(site1), (1, 0): _plain_site(site2)})
+    return orc.norm_tensor(cell, ((0, 0), (1, 0), k), a1q, a2q).contiguous()
+
+
 _EMULATED = ["gemm_ex", "quarter_tensor", "orthonormalize", "jacobi_svd", "rsvd", "projectors_from_usv", "absorb_corner1",
              "absorb_corner2", "absorb_edge", "absorb_edge_begin", "absorb_edge_finish", "permute_copy", "absmax", "frob_normalize",
-             "als_solve", "i8_supported"]
+             "als_solve", "i8_supported", "site_rdm", "bond_rdm", "norm_tensor"]
 
 
 @contextlib.contextmanager

@@ -48,13 +48,14 @@ def test_reference_ground_state_pins_through_b200_host_path(case):
         assert ref_moves.calls == 0, "evolve / renormalize issued CTMRG moves on the reference torch path"
 
 
-def test_evolve_matches_reference_torch_path():
+@pytest.mark.parametrize("als_method", ["cholesky", "pinv"])
+def test_evolve_matches_reference_torch_path(als_method):
     """The same short evolution on the reference torch path and through the b200 host path (same seed => same init noise and
     the same Omega stream): energies agree far below the physics tolerance; the torch path does use the reference mover."""
     Ipeps = _setup()
     base = {"dtype": "float64", "device": "cpu", "TN": {"nx": 2, "ny": 2, "dims": {"phys": 2, "bond": 2, "chi": 8}},
             "model": {"name": "heisenberg", "params": {"J": 1.0}}, "ctmrg": {"steps": 3, "disable_progressbar": True},
-            "evolution": {"disable_progressbar": True}}
+            "evolution": {"disable_progressbar": True, "als_method": als_method}}
 
     def run(b200):
         torch.manual_seed(11)

@@ -94,3 +94,19 @@ def test_readme_quickstart_on_b200():
     assert res[True]["Energy"] == pytest.approx(res[False]["Energy"], abs=1e-6)
     assert res[True]["Energy"] == pytest.approx(-0.6582813104072897, abs=1e-4)
     assert abs(res[True]["sz"]) == pytest.approx(abs(res[False]["sz"]), abs=1e-5)
+
+
+def test_evolve_with_als_pinv_matches_reference_torch():
+    """evolution.als_method = "pinv" (als_solver.py:226-228): routed to acetn_b200.evolution.ALSSolver.solve_pinv (host-driven loop on
+    the library's kernels); a short evolution agrees with the reference torch path on the same GPU, same seed."""
+    Ipeps = setup()
+    base = {"dtype": "float64", "device": "cuda", "TN": {"nx": 2, "ny": 2, "dims": {"phys": 2, "bond": 2, "chi": 12}},
+            "model": {"name": "heisenberg", "params": {"J": 1.0}}, "ctmrg": {"steps": 4}, "evolution": {"als_method": "pinv"}}
+    res = {}
+    for b200 in (False, True):
+        torch.manual_seed(3)
+        ip = Ipeps(_cuda_cfg(base, b200))
+        assert ip.config.evolution.als_method == "pinv"
+        ip.evolve(dtau=0.05, steps=5)
+        res[b200] = float(ip.measure()["Energy"])
+    assert res[True] == pytest.approx(res[False], abs=1e-8)

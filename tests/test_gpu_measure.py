@@ -58,3 +58,34 @@ def test_known_answer_energy_on_gpu(name):
     assert float(out["Energy"]) == pytest.approx(st["energy_csv"], rel=1e-10)
     for k, v in st["reference_measure"].items():
         assert float(out[k]) == pytest.approx(v, rel=1e-10, abs=1e-12)
+
+
+def test_rdms_with_unequal_chi_legs():
+    """Every chi leg with its own extent through acetn_b200_site_rdm / acetn_b200_bond_rdm (truncation gives chi' per projector,
+    SURVEY.md App. D2); the same ragged rings as the host-logic CPU test (tests/test_environment_host_cpu.py), on the real kernels."""
+    from tests.test_environment_host_cpu import _ragged_sites
+    D, d = 3, 2
+    A, B = _ragged_sites(D, d, 7)
+    cell = orc.Cell(2, 1, {}, {(0, 0): A, (1, 0): B})
+
+    class S:
+        def __init__(self, s):
+            self.s = s
+
+        def __getitem__(self, k):
+            return {"A": self.s.A.cuda(), "C": [c.cuda() for c in self.s.C], "E": [e.cuda() for e in self.s.E]}[k]
+
+        def bond_permute(self, k):
+            return self.s.bond_permute(k).cuda()
+
+    got = ops.bond_rdm(S(A), S(B), 0).cpu()
+    assert rel(got, orc.bond_rdm(cell, ((0, 0), (1, 0), 0))) < 1e-12
+    gg = torch.Generator().manual_seed(9)
+    R = lambda *s: torch.randn(*s, dtype=torch.float64, generator=gg)     # noqa: E731
+    a, b, c, e, g_, h, i, j = 2, 3, 4, 5, 6, 3, 5, 4
+    St = orc.Site(R(D, D, D, D, d), [R(c, g_), R(h, i), R(j, e), R(a, b)], [R(g_, h, D, D), R(i, j, D, D), R(e, a, D, D), R(b, c, D, D)])
+    ref = orc.site_rdm(orc.Cell(1, 1, {}, {(0, 0): St}), (0, 0))
+    got = ops.site_rdm([t.cuda() for t in St.C], [t.cuda() for t in St.E], St.A.cuda()).cpu()
+    assert rel(got, ref) < 1e-12
+    with pytest.raises(RuntimeError):                 # mismatched legs are rejected with the library's message
+        ops.site_rdm([t.cuda() for t in St.C][::-1], [t.cuda() for t in St.E], St.A.cuda())
