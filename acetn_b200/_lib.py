@@ -28,6 +28,7 @@ SIGNATURES = {
     "acetn_b200_gemm": (c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, P_i64, c_dbl, c_dbl, c_int, c_int, c_vp, c_sz, c_vp]),
     "acetn_b200_quarter_tensor_workspace_bytes": (c_sz, [c_i64] * 6),
     "acetn_b200_quarter_tensor": (c_int, [c_vp, c_vp, c_vp, c_vp, P_i64] + [c_i64] * 6 + [c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_quarter_tensor_enc": (c_int, [c_vp, c_vp, c_vp, c_vp, P_i64] + [c_i64] * 6 + [c_vp, c_vp, c_vp, c_sz, c_vp, c_sz, c_vp]),
     "acetn_b200_rsvd_workspace_bytes": (c_sz, [c_int, P_i64, P_i64, c_i64]),
     "acetn_b200_rsvd": (c_int, [c_int, ctypes.POINTER(c_vp), P_i64, P_i64, c_vp, c_i64, c_int, c_int, c_i64, c_dbl,
                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -31,6 +31,7 @@ struct FusedParams {
     const double* A; int64_t ax0, ax1, ap, ay0, ay1;       // strides of A for x=(f0,f1), p, y=(r,d)
     double* Y; int64_t out_s0, out_s1, oes0, oes1, oes2, oes3;
     double* absmax;
+    int32_t* colexp;       // optional (D = 8 kernel): colexp[b1 * D^2 + n] = max over (b0, y) of the binary exponent of Y, for the K7 encoding
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1) double_layer_fused_d8_kernel(const FusedParams p) {
@@ -60,6 +61,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) double_layer_fused_d8_kernel(con
         for (int i = 0; i < 8; i++)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(i * 8 * X_ROW * 8)), "l"(src + i * p.es0));
     };
+
+    // column exponents of the output for the K7 residue encoding (i8crt.cu): the 8 warps of the CTA hold the 64 rows y of a block,
+    // so the per-block column maximum is an 8-way shared-memory max, flushed with one global atomic max per column and block
+    __shared__ int cmx[FD2];
+    if (tid < FD2) cmx[tid] = 0;
 
     double vmax = 0.0;
     int64_t blk = blockIdx.x;
@@ -125,6 +131,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) double_layer_fused_d8_kernel(con
         {
             const int64_t b0 = blk / p.n1, b1 = blk - b0 * p.n1;
             double* Yb = p.Y + b0 * p.out_s0 + b1 * p.out_s1 + (int64_t)w * p.oes1 + (int64_t)lr * p.oes3;
+            int ef[2] = {0, 0};
 #pragma unroll
             for (int jn = 0; jn < 8; jn++) {
 #pragma unroll
@@ -132,10 +139,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) double_layer_fused_d8_kernel(con
                     double v = acc2[jn][e];
                     Yb[(int64_t)jn * p.oes0 + (int64_t)(2 * lc + e) * p.oes2] = v;
                     vmax = fmax(vmax, fabs(v));
+                    ef[e] = max(ef[e], (__double2hiint(v) >> 20) & 0x7ff);
+                }
+            }
+            if (p.colexp != nullptr) {
+                // this thread's columns: n = (dd = 2 lc + e, Dd = lr)
+                atomicMax(&cmx[(2 * lc) * FD + lr], ef[0]);
+                atomicMax(&cmx[(2 * lc + 1) * FD + lr], ef[1]);
+                __syncthreads();
+                if (tid < FD2) {
+                    const int m = cmx[tid];
+                    if (m > 0) atomicMax(p.colexp + b1 * FD2 + tid, m - 1022);
+                    cmx[tid] = 0;
                 }
             }
         }
-        __syncthreads();     // all warps are done with Xs[buf] before the next iteration refills it
+        __syncthreads();     // all warps are done with Xs[buf] (and cmx) before the next iteration refills it
     }
     cp_async_wait<0>();
     if (p.absmax) {
@@ -316,6 +335,9 @@ int launch_generic(const FusedParams& p, cudaStream_t s) {
 #define AB_FUSED_LIST(X) X(2, 2) X(3, 2) X(3, 3) X(4, 2) X(5, 2) X(6, 2) X(7, 2) X(7, 4)
 }  // namespace
 
+// 1 when the fused kernel for (D, d) can deliver the column exponents of its output (see FusedParams::colexp)
+int double_layer_fused_colexp_supported(int64_t D, int64_t d) { return (D == 8 && d == 2) ? 1 : 0; }
+
 int double_layer_fused_supported(int64_t D, int64_t d) {
     if (D == 8 && d == 2) return 1;
 #define AB_CASE(DD, dd) if (D == DD && d == dd) return 1;
@@ -326,7 +348,7 @@ int double_layer_fused_supported(int64_t D, int64_t d) {
 
 int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t in_s0, int64_t in_s1, const int64_t* in_es,
                               int order, const double* A, const int64_t* a_strides, int64_t D, int64_t d, double* Y,
-                              int64_t out_s0, int64_t out_s1, const int64_t* out_es, double* absmax, cudaStream_t s) {
+                              int64_t out_s0, int64_t out_s1, const int64_t* out_es, double* absmax, int32_t* colexp, cudaStream_t s) {
     if (!double_layer_fused_supported(D, d)) {
         set_error("double_layer_fused: no specialisation for D=%lld d=%lld", (long long)D, (long long)d);
         return ERR_UNSUPPORTED;
@@ -339,7 +361,9 @@ int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t i
     p.A = A; p.ax0 = a_strides[f0]; p.ax1 = a_strides[f1]; p.ap = a_strides[4]; p.ay0 = a_strides[2]; p.ay1 = a_strides[3];
     p.Y = Y; p.out_s0 = out_s0; p.out_s1 = out_s1; p.oes0 = out_es[0]; p.oes1 = out_es[1]; p.oes2 = out_es[2]; p.oes3 = out_es[3];
     p.absmax = absmax;
+    p.colexp = colexp;
     if (!(D == 8 && d == 2)) {
+        AB_REQUIRE(colexp == nullptr, "double_layer_fused: column exponents are produced by the D = 8, d = 2 kernel only");
 #define AB_CASE(DD, dd) if (D == DD && d == dd) return launch_generic<DD, dd>(p, s);
         AB_FUSED_LIST(AB_CASE)
 #undef AB_CASE

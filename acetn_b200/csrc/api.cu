@@ -17,9 +17,10 @@ size_t als_workspace_bytes(int nD, int bD, int pD);
 int als_solve_launch(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int nD, int bD, int pD,
                      int niter, double tol, double epsilon, int* info, void* wsp, size_t ws_bytes, cudaStream_t s);
 int double_layer_fused_supported(int64_t D, int64_t d);
+int double_layer_fused_colexp_supported(int64_t D, int64_t d);
 int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t in_s0, int64_t in_s1, const int64_t* in_es,
                               int order, const double* A, const int64_t* a_strides, int64_t D, int64_t d, double* Y,
-                              int64_t out_s0, int64_t out_s1, const int64_t* out_es, double* absmax, cudaStream_t s);
+                              int64_t out_s0, int64_t out_s1, const int64_t* out_es, double* absmax, int32_t* colexp, cudaStream_t s);
 }  // namespace ab200
 
 namespace {
@@ -54,11 +55,12 @@ size_t dl_workspace_bytes(int64_t n0, int64_t n1, int64_t D, int64_t d) {
     const int64_t D4 = D * D * D * D;
     return ws_round((size_t)(n0 * n1 * D4 * d) * 8) + 2 * ws_round((size_t)(D4 * d) * 8) + 4096;
 }
-int double_layer(const DoubleLayerArgs& a, double* absmax, void* wsp, size_t ws_bytes, cudaStream_t s) {
+int double_layer(const DoubleLayerArgs& a, double* absmax, void* wsp, size_t ws_bytes, cudaStream_t s, int32_t* colexp = nullptr) {
     const int64_t D = a.D, d = a.d, D4 = D * D * D * D;
     if (double_layer_fused_supported(D, d))
         return double_layer_fused_launch(a.X, a.n0, a.n1, a.in_s0, a.in_s1, a.in_es, a.order, a.A, a.a_s, D, d, a.Y,
-                                         a.out_s0, a.out_s1, a.out_es, absmax, s);
+                                         a.out_s0, a.out_s1, a.out_es, absmax, colexp, s);
+    AB_REQUIRE(colexp == nullptr, "double_layer: column exponents need the fused kernel");
     Workspace ws(wsp, ws_bytes);
     double* W = ws.take<double>((size_t)(a.n0 * a.n1 * D4 * d));
     double* bra = ws.take<double>((size_t)(D4 * d));
@@ -162,13 +164,15 @@ size_t acetn_b200_quarter_tensor_workspace_bytes(int64_t xa, int64_t xb, int64_t
     size_t g = maxz(gemm_workspace_bytes(q_gemm1(q, nullptr, nullptr, nullptr)), gemm_workspace_bytes(q_gemm2(q, nullptr, nullptr, nullptr)));
     return b + maxz(g, dl_workspace_bytes(xc, xe, D, d)) + 4096;
 }
-int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E1, const double* A, const int64_t* a_strides,
-                              int64_t xa, int64_t xb, int64_t xc, int64_t xe, int64_t D, int64_t d, int normalize, double* Q,
-                              double* absmax_out, void* wsp, size_t ws_bytes, void* stream) {
-    cudaStream_t s = S_(stream);
+static int quarter_tensor_impl(const double* C, const double* E2, const double* E1, const double* A, const int64_t* a_strides,
+                               int64_t xa, int64_t xb, int64_t xc, int64_t xe, int64_t D, int64_t d, int normalize, double* Q,
+                               double* absmax_out, void* enc_storage, size_t enc_bytes, void* wsp, size_t ws_bytes, cudaStream_t s) {
     QuarterDims q{xa, xb, xc, xe, D, d};
     const int64_t D2 = D * D, N2 = xe * D2, M2 = xc * D2;
     AB_REQUIRE(M2 < 2147483647LL && N2 < 2147483647LL, "quarter_tensor: chi*D^2 too large");
+    AB_REQUIRE(enc_storage == nullptr || !normalize, "quarter_tensor_enc: the encoding is taken from the un-normalised tensor (normalize must be 0)");
+    AB_REQUIRE(enc_storage == nullptr || i8_supported(M2, N2, 1), "quarter_tensor_enc: %lld x %lld is outside the INT8 engine's range", (long long)M2,
+               (long long)N2);
     Workspace ws(wsp, ws_bytes);
     double* T1 = ws.take<double>((size_t)(xa * M2));
     double* T2 = ws.take<double>((size_t)(M2 * N2));
@@ -188,10 +192,30 @@ int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E
     if (absmax_out) mx = absmax_out;
     if (want_max) AB_CHECK_CUDA(cudaMemsetAsync(mx, 0, 8, s));
     const bool fused = double_layer_fused_supported(D, d) != 0;
-    AB_TRY(double_layer(a, (want_max && fused) ? mx : nullptr, rest, rest_bytes, s));
+    // K7 encoding of the result: the fused D = 8 kernel delivers the column exponents from its epilogue (columns of Q = (e, d, D) =
+    // (block b1, n)), which saves the encoding one of its passes over the 2 GiB tensor
+    int32_t* colexp = nullptr;
+    const bool colexp_fused = enc_storage != nullptr && double_layer_fused_colexp_supported(D, d) != 0;
+    if (colexp_fused) AB_TRY(i8_colexp_reset_launch(enc_storage, M2, N2, &colexp, s));
+    AB_TRY(double_layer(a, (want_max && fused) ? mx : nullptr, rest, rest_bytes, s, colexp));
     if (want_max && !fused) AB_TRY(absmax_launch(Q, (size_t)(M2 * N2), mx, s));
     if (normalize) AB_TRY(scale_inv_launch(Q, (size_t)(M2 * N2), mx, s));
+    if (enc_storage != nullptr) {
+        I8Matrix e;
+        AB_TRY(i8_encode_launch(Q, M2, N2, N2, enc_storage, enc_bytes, &e, s, colexp_fused));
+    }
     return OK;
+}
+int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E1, const double* A, const int64_t* a_strides,
+                              int64_t xa, int64_t xb, int64_t xc, int64_t xe, int64_t D, int64_t d, int normalize, double* Q,
+                              double* absmax_out, void* wsp, size_t ws_bytes, void* stream) {
+    return quarter_tensor_impl(C, E2, E1, A, a_strides, xa, xb, xc, xe, D, d, normalize, Q, absmax_out, nullptr, 0, wsp, ws_bytes, S_(stream));
+}
+int acetn_b200_quarter_tensor_enc(const double* C, const double* E2, const double* E1, const double* A, const int64_t* a_strides,
+                                  int64_t xa, int64_t xb, int64_t xc, int64_t xe, int64_t D, int64_t d, double* Q, double* absmax_out,
+                                  void* enc_storage, size_t enc_bytes, void* wsp, size_t ws_bytes, void* stream) {
+    AB_REQUIRE(enc_storage != nullptr, "quarter_tensor_enc: enc_storage must not be NULL");
+    return quarter_tensor_impl(C, E2, E1, A, a_strides, xa, xb, xc, xe, D, d, 0, Q, absmax_out, enc_storage, enc_bytes, wsp, ws_bytes, S_(stream));
 }
 
 // ---- orthonormalise / jacobi ---------------------------------------------------------------------------------------------

@@ -1,4 +1,5 @@
-// K7 -- FP64-exact "big x thin" products on the INT8 tensor cores (sm_100a tcgen05.mma kind::i8).
+// K7 -- FP64-accurate (normwise; exact products of P-bit fixed-point operands) "big x thin" products on the INT8 tensor cores
+// (sm_100a tcgen05.mma kind::i8).
 //
 // The 12+1 thin products of a half-system projector (fused_matmul_svd_lowrank.py:33-46, projectors.py:172) multiply the
 // same two 16384 x 16384 quarter tensors by 258-column matrices.  The FP64 DMMA pipe tops out at 37 TFLOP/s; the INT8
@@ -7,8 +8,10 @@
 //
 //   1. two-sided power-of-two scaling turns both operands into integer matrices of P <= 54 bits
 //        a'_ij = rint(Q_ij 2^(P - r_i - c_j)),   b'_jz = rint(Y_jz 2^(c_j) 2^(P - e_z))       (|a'|,|b'| <= 2^P)
-//      r_i / c_j = row / column binary exponents of Q (c_j taken after the row scaling), e_z = column exponent of the
-//      row-shifted Y.  The only rounding of the whole product happens here: 2^-54 relative to the row/column scale.
+//      c_j / r_i = column / row binary exponents of Q (c_j = exponent of the largest entry of column j; r_i taken after the
+//      column scaling, so r_i <= 0), e_z = column exponent of the row-shifted Y.  The only rounding of the whole product
+//      happens here: 2^-P relative to the row x column scale, i.e. the result is NORMWISE FP64-accurate per row / column
+//      scale, not componentwise (entries more than 2^-P below their row-and-column scale are flushed).
 //   2. a', b' are reduced modulo 16 pairwise coprime moduli m_l <= 256 (a': residues in [0,m) as uint8, b': balanced
 //      residues as int8): one pass over Q per site-move (i8_encode), one cheap pass over each thin operand.
 //   3. per modulus an exact UINT8 x INT8 -> INT32 GEMM on the tensor cores (k * 255 * 128 < 2^31 for k <= 65535), epilogue
@@ -90,32 +93,17 @@ __device__ __forceinline__ void residues16u(long long v, int r[I8_NMOD]) {
 // ---------------------------------------------------------------------------------------------------------------------
 // encode: exponents
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) row_exp_kernel(const double* __restrict__ Q, int64_t cols, int64_t ldq, int32_t* __restrict__ rowexp) {
-    const double* row = Q + (int64_t)blockIdx.x * ldq;
-    int mx = 0;
-    for (int64_t j = threadIdx.x; j < cols; j += 256) mx = max(mx, exp_field(row[j]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    __shared__ int sm[8];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) mx = max(mx, sm[w]);
-        rowexp[blockIdx.x] = mx == 0 ? EXP_NONE : mx - 1022;       // |x| < 2^rowexp on the row
-    }
-}
-// colexp[j] = max_i (exponent(Q_ij) - rowexp[i])   (<= 0); colexp pre-set to a very negative value
-__global__ void __launch_bounds__(256) col_exp_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
-                                                      const int32_t* __restrict__ rowexp, int32_t* __restrict__ colexp) {
+// colexp[j] = max_i exponent(Q_ij)  (|Q_ij| < 2^colexp[j]; EXP_NONE for an all-zero column); colexp pre-set to EXP_NONE.
+// Only used when the producer of Q did not deliver the column exponents itself (the fused double-layer kernel does, from its
+// epilogue: absorb_fused.cu).
+__global__ void __launch_bounds__(256) col_max_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
+                                                      int32_t* __restrict__ colexp) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.y * 64;
     if (j >= cols) return;
-    int mx = EXP_NONE;
-    for (int64_t i = i0; i < i0 + 64 && i < rows; i++) {
-        int ef = exp_field(Q[i * ldq + j]);
-        if (ef != 0) mx = max(mx, ef - 1022 - rowexp[i]);
-    }
-    if (mx > EXP_NONE) atomicMax(colexp + j, mx);
+    int mx = 0;
+    for (int64_t i = i0; i < i0 + 64 && i < rows; i++) mx = max(mx, exp_field(Q[i * ldq + j]));
+    if (mx > 0) atomicMax(colexp + j, mx - 1022);
 }
 __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,19 +111,19 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// encode: residues of the big matrix.  Thread = 8 consecutive columns of one row; 16 eight-byte stores (one per plane).
+// encode: one CTA per row of the big matrix.  Pass A reads the row once from HBM and finds its exponent after the column
+// scaling, r_i = max_j (exponent(Q_ij) - c_j) <= 0; pass B re-reads it (128 KB: an L2 hit) and writes the 16 residue planes.
+// One HBM pass over Q (8 B/element read + 16 B/element written) instead of three.  Thread = 8 consecutive columns per step.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) encode_big_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
-                                                         const int32_t* __restrict__ rowexp, const int32_t* __restrict__ colexp, int P,
-                                                         int8_t* __restrict__ res, int64_t ld, int vec_ok) {
-    const int64_t i = blockIdx.y;
-    const int64_t j0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-    if (j0 >= ld) return;
-    const int re = rowexp[i];
+// residues of 8 consecutive columns of one row -> 16 eight-byte stores (one per plane).  Deliberately NOT inlined: as straight-line
+// code it needs 64 registers (the moduli tables stay constant-bank operands); inlined into the row loop the compiler hoists the 80
+// table entries into registers and spills.
+__device__ __noinline__ void encode_chunk8(const double* __restrict__ row, const int32_t* __restrict__ colexp, int64_t j0, int64_t cols,
+                                           int re, int P, int8_t* __restrict__ dst, int64_t plane, int vec_ok) {
     double x[8];
     int ce[8];
     if (vec_ok && j0 + 8 <= cols) {
-        const double2* src = reinterpret_cast<const double2*>(Q + i * ldq + j0);
+        const double2* src = reinterpret_cast<const double2*>(row + j0);
         const int4* csrc = reinterpret_cast<const int4*>(colexp + j0);
 #pragma unroll
         for (int c = 0; c < 4; c++) { double2 t = __ldcs(src + c); x[2 * c] = t.x; x[2 * c + 1] = t.y; }
@@ -145,7 +133,7 @@ __global__ void __launch_bounds__(256) encode_big_kernel(const double* __restric
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             const int64_t j = j0 + c;
-            x[c] = j < cols ? Q[i * ldq + j] : 0.0;
+            x[c] = j < cols ? row[j] : 0.0;
             ce[c] = j < cols ? colexp[j] : EXP_NONE;
         }
     }
@@ -160,14 +148,54 @@ __global__ void __launch_bounds__(256) encode_big_kernel(const double* __restric
         residues16u(v, r);
 #pragma unroll
         for (int l = 0; l < I8_NMOD; l++) {
-            if (c < 4) w0[l] |= (uint32_t)r[l] << (8 * (c & 3));
-            else w1[l] |= (uint32_t)r[l] << (8 * (c & 3));
+            // residues of different columns occupy different bytes: a multiply-add packs them (one IMAD instead of SHF + LOP3)
+            if (c < 4) w0[l] += (uint32_t)r[l] * (1u << (8 * (c & 3)));
+            else w1[l] += (uint32_t)r[l] * (1u << (8 * (c & 3)));
         }
     }
-    const int64_t plane = rows * ld;
 #pragma unroll
-    for (int l = 0; l < I8_NMOD; l++)
-        __stcs(reinterpret_cast<uint2*>(res + l * plane + i * ld + j0), make_uint2(w0[l], w1[l]));
+    for (int l = 0; l < I8_NMOD; l++) __stcs(reinterpret_cast<uint2*>(dst + l * plane), make_uint2(w0[l], w1[l]));
+}
+
+__global__ void __launch_bounds__(256, 3) encode_rows_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
+                                                             int32_t* __restrict__ rowexp, const int32_t* __restrict__ colexp, int P,
+                                                             int8_t* __restrict__ res, int64_t ld, int vec_ok) {
+    const int64_t i = blockIdx.x;
+    const double* row = Q + i * ldq;
+    __shared__ int sm[8];
+    // ---- pass A
+    int mx = EXP_NONE;
+    if (vec_ok) {
+#pragma unroll 2
+        for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < cols; j0 += 1024) {
+            if (j0 + 4 <= cols) {
+                const double2 t0 = __ldg(reinterpret_cast<const double2*>(row + j0)), t1 = __ldg(reinterpret_cast<const double2*>(row + j0 + 2));
+                const int4 c = __ldg(reinterpret_cast<const int4*>(colexp + j0));
+                int e0 = exp_field(t0.x), e1 = exp_field(t0.y), e2 = exp_field(t1.x), e3 = exp_field(t1.y);
+                if (e0) mx = max(mx, e0 - 1022 - c.x);
+                if (e1) mx = max(mx, e1 - 1022 - c.y);
+                if (e2) mx = max(mx, e2 - 1022 - c.z);
+                if (e3) mx = max(mx, e3 - 1022 - c.w);
+            } else {
+                for (int64_t j = j0; j < cols; j++) { int e = exp_field(row[j]); if (e) mx = max(mx, e - 1022 - colexp[j]); }
+            }
+        }
+    } else {
+        for (int64_t j = threadIdx.x; j < cols; j += 256) { int e = exp_field(row[j]); if (e) mx = max(mx, e - 1022 - colexp[j]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = max(mx, sm[w]);
+    const int re = mx;                                        // EXP_NONE for an all-zero row
+    if (threadIdx.x == 0) rowexp[i] = re;
+    // ---- pass B
+    const int64_t plane = rows * ld;
+#pragma unroll 1
+    for (int64_t j0 = (int64_t)threadIdx.x * 8; j0 < ld; j0 += 2048) encode_chunk8(row, colexp, j0, cols, re, P, res + i * ld + j0, plane, vec_ok);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -434,182 +462,6 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// CTA-pair version (tcgen05.mma.cta_group::2, M = 256 over two SMs of a TPC) -- experimental, opt-in (see i8_pair_mode).
-// Per 128-deep K block the single-CTA kernel writes 50 KB by TMA and the tensor core reads A twice (N = 128 + 144) plus the
-// whole B tile.  In pair mode each CTA stages its own 128 A rows and only HALF of the B tile (the MMA reads the other half
-// from the peer SM), so TMA writes drop to 33 KB and operand reads by a quarter.  Measured: no gain (the IMMA pipe, 70 %
-// active under the power cap, is the limiter, not shared memory).
-//   * both CTAs issue cp.async.bulk.tensor...cta_group::2 loads whose complete_tx lands on the LEADER's (rank 0) full barrier;
-//   * the leader's elected thread issues the MMAs and multicasts tcgen05.commit to the empty / tmem_full barriers of both CTAs;
-//   * each CTA drains its own 128 TMEM lanes; the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y, int z) {
-    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"((unsigned long long)map), "r"(leader_bar), "r"(x), "r"(y), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__host__ __device__ constexpr uint32_t i8_idesc_pair(int n, int a_mn_major) {
-    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
-                    const GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-    const uint32_t bar_tmem_full = bar_base + 16u * (uint32_t)p.stages;
-    const uint32_t bar_tmem_empty = bar_tmem_full + 8;
-    const uint32_t tmem_holder = bar_tmem_empty + 8;
-    uint32_t* tmem_holder_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int h1 = p.n1 >> 1, h2 = p.n2 >> 1;          // B rows of each MMA staged by this CTA
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; s++) {
-            mbar_init(bar_base + 16u * s, 1);           // full: the leader's arrive.expect_tx (bytes of both CTAs)
-            mbar_init(bar_base + 16u * s + 8, 1);       // empty: one multicast tcgen05.commit
-        }
-        mbar_init(bar_tmem_full, 1);
-        mbar_init(bar_tmem_empty, 8);                   // 4 epilogue warps x 2 CTAs (used on the leader only)
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_holder), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder_ptr;
-    const int total = I8_NMOD * p.mtiles;               // mtiles counts 256-row tiles here
-    const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer (both CTAs) =====
-            int s = 0;
-            uint32_t ph = 0;
-            const uint32_t tx_pair = 2u * (uint32_t)(A_TILE_BYTES + (h1 + h2) * 128);
-            for (int item = pair; item < total; item += npairs) {
-                const int l = item / p.mtiles, mt = item - l * p.mtiles;
-                const int m0 = mt * 256 + (int)rank * 128;
-                for (int kc = 0; kc < p.nk; kc++) {
-                    const uint32_t full = bar_base + 16u * s, empty = full + 8;
-                    const uint32_t full_leader = mapa_rank(full, 0);
-                    mbar_wait(empty, ph ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(full, tx_pair);
-                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                    if (!p.trans) tma_load_3d_2sm(sa, &tmA, full_leader, kc * 128, m0, l);
-                    else tma_load_3d_2sm(sa, &tmA, full_leader, m0, kc * 128, l);
-                    tma_load_3d_2sm(sa + A_TILE_BYTES, &tmB1, full_leader, kc * 128, (int)rank * h1, l);
-                    if (h2 > 0) tma_load_3d_2sm(sa + A_TILE_BYTES + (uint32_t)(h1 * 128), &tmB2, full_leader, kc * 128, p.n1 + (int)rank * h2, l);
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ===== MMA issuer (leader CTA only) =====
-            const uint32_t idesc1 = i8_idesc_pair(p.n1, p.trans);
-            const uint32_t idesc2 = i8_idesc_pair(p.n2 > 0 ? p.n2 : 32, p.trans);
-            const uint32_t a_kstep = p.trans ? (32u * 128u) >> 4 : 32u >> 4;
-            int s = 0;
-            uint32_t ph = 0, tph = 0;
-            for (int item = pair; item < total; item += npairs) {
-                mbar_wait(bar_tmem_empty, tph ^ 1);
-                tc_fence_after();
-                for (int kc = 0; kc < p.nk; kc++) {
-                    const uint32_t full = bar_base + 16u * s, empty = full + 8;
-                    mbar_wait(full, ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                    const uint32_t sb = sa + A_TILE_BYTES;
-                    const uint64_t da = smem_desc(sa, p.trans ? 16384u : 16u, 1024u);
-                    const uint64_t db1 = smem_desc(sb, 16u, 1024u);
-                    const uint64_t db2 = smem_desc(sb + (uint32_t)h1 * 128u, 16u, 1024u);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
-                        const uint32_t acc = (kc | k4) != 0;
-                        tc_mma_i8_pair(tmem_base, da + (uint64_t)(a_kstep * k4), db1 + (uint64_t)(2 * k4), idesc1, acc);
-                        if (p.n2 > 0)
-                            tc_mma_i8_pair(tmem_base + (uint32_t)p.n1, da + (uint64_t)(a_kstep * k4), db2 + (uint64_t)(2 * k4), idesc2, acc);
-                    }
-                    tc_commit_pair(empty);
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
-                }
-                tc_commit_pair(bar_tmem_full);
-                tph ^= 1;
-            }
-        }
-    } else {
-        // ===== epilogue (both CTAs, own 128 TMEM lanes) =====
-        const int quarter = warp & 3;
-        const uint32_t tmem_empty_leader = mapa_rank(bar_tmem_empty, 0);
-        uint32_t tph = 0;
-        for (int item = pair; item < total; item += npairs) {
-            const int l = item / p.mtiles, mt = item - l * p.mtiles;
-            const int m = c_mod[l], lo = c_lo[l];
-            const float inv = c_inv[l];
-            mbar_wait(bar_tmem_full, tph);
-            tc_fence_after();
-            const int64_t row = (int64_t)mt * 256 + (int64_t)rank * 128 + quarter * 32 + lane;
-            int8_t* orow = p.out + ((int64_t)l * p.m_out + row) * p.npad;
-            for (int c0 = 0; c0 < p.npad; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-                uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < 16; c++) {
-                    int r = bal_mod((int)v[c], m, lo, inv);
-                    w[c >> 2] |= (uint32_t)(r & 0xff) << (8 * (c & 3));
-                }
-                if (row < p.m_out) *reinterpret_cast<uint4*>(orow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-            tph ^= 1;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // CRT reconstruction.  Thread = 4 consecutive columns of one output row.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ res, int64_t m, int npad, int q, const int32_t* __restrict__ erow,
@@ -716,24 +568,46 @@ size_t i8_encoded_bytes(int64_t rows, int64_t cols) {
     return ws_round((size_t)I8_NMOD * (size_t)rows * (size_t)i8_ld(cols)) + ws_round((size_t)rows * 4) + ws_round((size_t)cols * 4) + 1024;
 }
 
-int i8_encode_launch(const double* Q, int64_t rows, int64_t cols, int64_t ldq, void* storage, size_t storage_bytes, I8Matrix* enc,
-                     cudaStream_t s) {
-    AB_REQUIRE(i8_supported(rows, cols, 1), "i8_encode: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
-    Workspace ws(storage, storage_bytes);
-    const int64_t ld = i8_ld(cols);
-    int8_t* res = ws.take<int8_t>((size_t)I8_NMOD * rows * ld);
-    int32_t* rowexp = ws.take<int32_t>((size_t)rows);
-    int32_t* colexp = ws.take<int32_t>((size_t)cols);
-    if (ws.overflow) { set_error("i8_encode: storage too small (%zu needed, %zu given)", ws.used, storage_bytes); return ERR_WORKSPACE; }
-    const int P = i8_operand_bits(rows > cols ? rows : cols);
-    row_exp_kernel<<<(unsigned)rows, 256, 0, s>>>(Q, cols, ldq, rowexp);
-    AB_LAUNCHED();
+void i8_carve(void* storage, int64_t rows, int64_t cols, int8_t** res, int32_t** rowexp, int32_t** colexp) {
+    I8Matrix e = i8_view(storage, rows, cols);
+    *res = const_cast<int8_t*>(e.res); *rowexp = const_cast<int32_t*>(e.rowexp); *colexp = const_cast<int32_t*>(e.colexp);
+}
+
+int i8_colexp_reset_launch(void* storage, int64_t rows, int64_t cols, int32_t** colexp_out, cudaStream_t s) {
+    int8_t* res; int32_t *rowexp, *colexp;
+    i8_carve(storage, rows, cols, &res, &rowexp, &colexp);
     fill_i32_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(colexp, (int)cols, EXP_NONE);
     AB_LAUNCHED();
-    col_exp_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)((rows + 63) / 64)), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp);
-    AB_LAUNCHED();
+    *colexp_out = colexp;
+    return OK;
+}
+
+int i8_encode_launch(const double* Q, int64_t rows, int64_t cols, int64_t ldq, void* storage, size_t storage_bytes, I8Matrix* enc,
+                     cudaStream_t s, bool colexp_ready) {
+    AB_REQUIRE(i8_supported(rows, cols, 1), "i8_encode: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+    AB_REQUIRE(storage != nullptr && storage_bytes >= i8_encoded_bytes(rows, cols), "i8_encode: storage too small (%zu needed, %zu given)",
+               i8_encoded_bytes(rows, cols), storage_bytes);
+    int8_t* res; int32_t *rowexp, *colexp;
+    i8_carve(storage, rows, cols, &res, &rowexp, &colexp);
+    const int64_t ld = i8_ld(cols);
+    const int P = i8_operand_bits(rows > cols ? rows : cols);
+    if (!colexp_ready) {
+        // no producer-side column exponents: one extra pass over Q
+        fill_i32_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(colexp, (int)cols, EXP_NONE);
+        AB_LAUNCHED();
+        col_max_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)((rows + 63) / 64)), 256, 0, s>>>(Q, rows, cols, ldq, colexp);
+        AB_LAUNCHED();
+    }
     const int vec_ok = (ldq % 2 == 0) && (((uintptr_t)Q & 15) == 0) && (((uintptr_t)colexp & 15) == 0);
-    encode_big_kernel<<<dim3((unsigned)((ld / 8 + 255) / 256), (unsigned)rows), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld, vec_ok);
+    // pass B of a row must find the row in L2: bound the rows in flight (CTAs per SM x SMs x 8 B x cols) to about half of the 126 MB
+    // L2 by padding the dynamic shared memory request (ACETN_B200_I8_ENC_CTAS overrides the CTAs per SM: dev tools only)
+    static const int ctas_env = env_int("ACETN_B200_I8_ENC_CTAS");
+    int per_sm = ctas_env > 0 ? ctas_env : (int)((size_t)(60 << 20) / ((size_t)device_sm_count() * 8 * (size_t)cols));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const size_t pad_smem = per_sm >= 8 ? 0 : (size_t)(220 * 1024) / per_sm - 1024;
+    AB_ENSURE_SMEM(encode_rows_kernel, 220 * 1024);
+    encode_rows_kernel<<<(unsigned)rows, 256, pad_smem, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld, vec_ok);
     AB_LAUNCHED();
     enc->res = res; enc->rowexp = rowexp; enc->colexp = colexp; enc->rows = rows; enc->cols = cols; enc->ld = ld; enc->P = P;
     return OK;
@@ -751,73 +625,38 @@ int i8_thin_encode_launch(const double* Y, int64_t k, int64_t q, int64_t ldy, co
     return OK;
 }
 
-// 0 = single-CTA kernel (default), 1 = CTA-pair kernel; ACETN_B200_I8_PAIR=1 opts in (read once).
-// EXPERIMENTAL: the pair kernel is bit-exact in isolation (tools/i8_check.py, all GPU tests) but measured no faster (1.19 vs
-// 1.18 ms per thin product: the INT8 pipe is clock/power bound, not shared-memory bound), and bench.py, which runs four
-// projector tasks on four streams, hung with it -- unresolved, hence never selected by default.
-int i8_pair_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("ACETN_B200_I8_PAIR");
-        mode = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return mode;
-}
-
 int i8_gemm_launch(const int8_t* Ares, int64_t rows, int64_t cols, int64_t ld, bool adjoint, const int8_t* Bres, int64_t ldk, int npad,
                    int8_t* Cres, cudaStream_t s) {
     AB_REQUIRE(npad % 16 == 0 && npad >= 16 && npad <= I8_MAX_THIN, "i8_gemm: npad must be a multiple of 16 in [16, %d]", I8_MAX_THIN);
     const int64_t m_out = adjoint ? cols : rows, kdim = adjoint ? rows : cols;
     AB_REQUIRE(kdim <= 65535, "i8_gemm: contraction length %lld exceeds the INT32 accumulator bound", (long long)kdim);
-    const bool pair = i8_pair_mode() != 0 && m_out > 128;
     GemmParams p;
     p.out = Cres; p.m_out = m_out; p.nk = (int)((kdim + 127) / 128); p.trans = adjoint ? 1 : 0;
     p.npad = npad;
     const int sms = device_sm_count();
     const int smem_budget = 227 * 1024 - 1024 - 256;
-    CUtensorMap tmA, tmB, tmB2;
+    CUtensorMap tmA, tmB;
     AB_TRY(make_map(&tmA, Ares, cols, rows, ld, I8_NMOD, 128));
-    if (!pair) {
-        p.mtiles = (int)((m_out + 127) / 128);
-        if (npad <= 256) { p.n1 = npad; p.n2 = 0; p.b_box_rows = npad; p.b_loads = 1; }
-        else { p.n1 = 128; p.n2 = npad - 128; p.b_box_rows = npad / 2; p.b_loads = 2; }
-        // tuning knobs (dev tools only): ACETN_B200_I8_N1 = columns of the first MMA when the tile needs two, ACETN_B200_I8_STAGES
-        static const int dbg_n1 = env_int("ACETN_B200_I8_N1"), dbg_stages = env_int("ACETN_B200_I8_STAGES");
-        if (p.n2 > 0 && dbg_n1 >= 16 && dbg_n1 <= 256 && dbg_n1 % 16 == 0 && npad - dbg_n1 >= 16) { p.n1 = dbg_n1; p.n2 = npad - dbg_n1; }
-        p.stage_bytes = (A_TILE_BYTES + npad * 128 + 1023) / 1024 * 1024;
-        p.stages = smem_budget / p.stage_bytes;
-        if (p.stages > 8) p.stages = 8;
-        if (dbg_stages >= 2 && dbg_stages < p.stages) p.stages = dbg_stages;
-        AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
-        const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
-        AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
-        AB_ENSURE_SMEM(i8_gemm_kernel, smem_bytes);
-        int grid = I8_NMOD * p.mtiles;
-        if (grid > sms) grid = sms;
-        i8_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, p);
-        AB_LAUNCHED();
-        return OK;
-    }
-    // CTA pair: 256-row tiles; every MMA's N is a multiple of 16 so that each CTA stages N/2 (a multiple of 8) B rows
-    p.mtiles = (int)((m_out + 255) / 256);
-    if (npad <= 256) { p.n1 = npad; p.n2 = 0; }
-    else { p.n1 = 128; p.n2 = npad - 128; }
-    AB_REQUIRE(p.n1 % 16 == 0 && p.n2 % 16 == 0, "i8_gemm: pair mode needs N halves that are multiples of 8");
-    p.b_box_rows = p.n1 / 2; p.b_loads = p.n2 > 0 ? 2 : 1;
-    p.stage_bytes = (A_TILE_BYTES + (npad / 2) * 128 + 1023) / 1024 * 1024;
+    p.mtiles = (int)((m_out + 127) / 128);
+    if (npad <= 256) { p.n1 = npad; p.n2 = 0; p.b_box_rows = npad; p.b_loads = 1; }
+    else { p.n1 = 128; p.n2 = npad - 128; p.b_box_rows = npad / 2; p.b_loads = 2; }
+    // tuning knobs (dev tools only): ACETN_B200_I8_N1 = columns of the first MMA when the tile needs two, ACETN_B200_I8_STAGES.
+    // Measured (profiles/r02_k7_stage_probe.txt): 2 / 3 / 4 stages = 1.67 / 1.24 / 1.18 ms per product -- four stages (all that fit)
+    // cover the load latency.  A CTA-pair variant (tcgen05.mma.cta_group::2, half of the thin-operand tile per CTA, 6 stages) measured
+    // the same 1.19 ms: the kernel is bound by the INT8 pipe under the power cap, not by shared-memory fill; it was removed.
+    static const int dbg_n1 = env_int("ACETN_B200_I8_N1"), dbg_stages = env_int("ACETN_B200_I8_STAGES");
+    if (p.n2 > 0 && dbg_n1 >= 16 && dbg_n1 <= 256 && dbg_n1 % 16 == 0 && npad - dbg_n1 >= 16) { p.n1 = dbg_n1; p.n2 = npad - dbg_n1; }
+    p.stage_bytes = (A_TILE_BYTES + npad * 128 + 1023) / 1024 * 1024;
     p.stages = smem_budget / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
+    if (dbg_stages >= 2 && dbg_stages < p.stages) p.stages = dbg_stages;
+    AB_REQUIRE(p.stages >= 2, "i8_gemm: tile does not fit shared memory");
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + 256;
-    AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.n1 / 2));
-    AB_TRY(make_map(&tmB2, Bres, kdim, npad, ldk, I8_NMOD, p.n2 > 0 ? p.n2 / 2 : 8));
-    static size_t smem_set2 = 0;
-    if (smem_bytes > smem_set2) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        smem_set2 = smem_bytes;
-    }
-    int pairs = I8_NMOD * p.mtiles;
-    if (pairs > sms / 2) pairs = sms / 2;
-    i8_gemm_pair_kernel<<<2 * pairs, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, tmB2, p);
+    AB_TRY(make_map(&tmB, Bres, kdim, npad, ldk, I8_NMOD, p.b_box_rows));
+    AB_ENSURE_SMEM(i8_gemm_kernel, smem_bytes);
+    int grid = I8_NMOD * p.mtiles;
+    if (grid > sms) grid = sms;
+    i8_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, s>>>(tmA, tmB, p);
     AB_LAUNCHED();
     return OK;
 }

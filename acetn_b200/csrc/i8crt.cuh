@@ -25,8 +25,12 @@ bool i8_supported(int64_t rows, int64_t cols, int64_t q);
 size_t i8_encoded_bytes(int64_t rows, int64_t cols);
 I8Matrix i8_view(const void* storage, int64_t rows, int64_t cols);   // the carve i8_encode_launch used            // residues + exponents, as carved by i8_encode_launch
 // Q (rows x cols FP64, row pitch ldq) -> enc (I8Matrix pointing into `storage`, which must hold i8_encoded_bytes())
+// colexp_ready: the column exponents (max_i exponent(Q_ij), EXP_NONE = -1000000 for an all-zero column) have already been written
+// into the storage by the producer of Q (i8_colexp_reset_launch + atomic max from the producing kernel's epilogue)
 int i8_encode_launch(const double* Q, int64_t rows, int64_t cols, int64_t ldq, void* storage, size_t storage_bytes, I8Matrix* enc,
-                     cudaStream_t s);
+                     cudaStream_t s, bool colexp_ready = false);
+// colexp array inside `storage`, reset to "all zero"; a producer then raises entry j with atomicMax(exponent - 1022)
+int i8_colexp_reset_launch(void* storage, int64_t rows, int64_t cols, int32_t** colexp_out, cudaStream_t s);
 size_t i8_matmul_workspace_bytes(int64_t rows, int64_t cols, int64_t q);
 // out (rows x q) = Q * Y (Y: cols x q)            adjoint = false
 // out (cols x q) = Q^T * Y (Y: rows x q)          adjoint = true

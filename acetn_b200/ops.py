@@ -106,10 +106,12 @@ def matmul(A, B, transpose_a=False, force_tile=0, force_splitk=0, out=None):
     return gemm_ex(M, N, K, 1, A, B, C, idx, force_tile=force_tile, force_splitk=force_splitk)
 
 
-def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, out=None):
+def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, out=None, enc_storage=None):
     """projectors.py:36-60.  C (xa,xb), E2 (xb,xc,D,D), E1 (xe,xa,D,D), A_view = bond_permute(k) (strided view).
     absmax: optional 1-element device tensor receiving max|Q| of the un-normalised tensor.
-    out: optional flat FP64 device buffer (>= numel of Q) that receives Q (a task slot of the phase scheduler)."""
+    out: optional flat FP64 device buffer (>= numel of Q) that receives Q (a task slot of the phase scheduler).
+    enc_storage: uint8 device buffer (>= i8_encoded_bytes) -> the K7 residue encoding of Q is produced in the same call
+    (acetn_b200_quarter_tensor_enc; requires normalize=False) and an I8Encoded is returned as third value."""
     dev = _require_cuda(C, E2, E1, A_view)
     C, E2, E1 = C.contiguous(), E2.contiguous(), E1.contiguous()
     xa, xb = C.shape
@@ -125,6 +127,15 @@ def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, 
         Q = torch.empty(xc * D * D, xe * D * D, dtype=torch.float64, device=dev)
     nb = lib.acetn_b200_quarter_tensor_workspace_bytes(xa, xb, xc, xe, D, d)
     ws = _ws(dev, nb, stream)
+    if enc_storage is not None:
+        if normalize:
+            raise ValueError("quarter_tensor: the K7 encoding is taken from the un-normalised tensor (normalize=False)")
+        with torch.cuda.device(dev):
+            st = lib.acetn_b200_quarter_tensor_enc(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
+                                                   _p(Q), _p(absmax) if absmax is not None else None, _p(enc_storage), enc_storage.numel(),
+                                                   _p(ws), ws.numel(), _stream(dev, stream))
+        _lib.check(st, "quarter_tensor_enc")
+        return Q, (xc, D, D, xe, D, D), I8Encoded(enc_storage, Q.shape[0], Q.shape[1])
     with torch.cuda.device(dev):
         st = lib.acetn_b200_quarter_tensor(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
                                            1 if normalize else 0, _p(Q), _p(absmax) if absmax is not None else None, _p(ws), ws.numel(),

@@ -44,7 +44,7 @@ class ProjectorCalculator:
             raise ValueError(f"Invalid ctmrg projector type: {self.projectors} provided.")
 
     @staticmethod
-    def make_quarter_tensor(site_tensor, k, normalize=True, stream=None, absmax=None, out=None):
+    def make_quarter_tensor(site_tensor, k, normalize=True, stream=None, absmax=None, out=None, enc_storage=None):
         """projectors.py:36-60 -> (Q matrix (chi D^2, chi D^2), 6-tuple shape).
         normalize=False skips the max-abs division (projectors.py:59): s/s[0], U and V are invariant under a rescaling
         of Q1/Q4, and the internal callers re-apply the factor 1/max|Q| to the small projector instead (absmax), which
@@ -53,7 +53,13 @@ class ProjectorCalculator:
         ck = site_tensor['C'][(0 + k) % 4]
         ek1 = site_tensor['E'][(3 + k) % 4]
         ek2 = site_tensor['E'][(0 + k) % 4]
-        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax, out=out)
+        return ops.quarter_tensor(ck, ek2, ek1, ak, normalize=normalize, stream=stream, absmax=absmax, out=out, enc_storage=enc_storage)
+
+    @staticmethod
+    def quarter_shape(site_tensor, k):
+        """(rows, cols) of make_quarter_tensor(site_tensor, k)."""
+        D = site_tensor['A'].shape[0]
+        return site_tensor['E'][(0 + k) % 4].shape[1] * D * D, site_tensor['E'][(3 + k) % 4].shape[0] * D * D
 
     @staticmethod
     def quarter_numel(site_tensor, k):
@@ -153,16 +159,24 @@ class ProjectorCalculator:
             omega = self.draw_omega(ipeps, sites, k)
         sa = bulk if (bulk is not None and stream is not None) else stream
         mx = torch.empty(2, dtype=omega.dtype, device=omega.device)   # zeroed by the library on the side stream
-        o1 = slot.buffer("Q1", self.quarter_numel(st1, k), omega.dtype, omega.device) if slot is not None else None
-        o4 = slot.buffer("Q4", self.quarter_numel(st4, k + 3), omega.dtype, omega.device) if slot is not None else None
-        Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1], out=o1)
-        Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2], out=o4)
+        dev = omega.device
+        n1, n4 = self.quarter_numel(st1, k), self.quarter_numel(st4, k + 3)
+        o1 = slot.buffer("Q1", n1, omega.dtype, dev) if slot is not None else None
+        o4 = slot.buffer("Q4", n4, omega.dtype, dev) if slot is not None else None
+        m1, m4 = self.quarter_shape(st1, k), self.quarter_shape(st4, k + 3)
         encs = None
-        if self._use_i8([tuple(Q1.shape), tuple(Q4.shape)], omega.shape[1]):
-            # K7: both quarter tensors are encoded once (16 int8 residue planes) and serve all 13 thin products
-            s1b = slot.buffer("enc1", ops.i8_encoded_bytes(*Q1.shape), torch.uint8, omega.device) if slot is not None else None
-            s4b = slot.buffer("enc4", ops.i8_encoded_bytes(*Q4.shape), torch.uint8, omega.device) if slot is not None else None
-            encs = [ops.i8_encode(Q1, stream=sa, storage=s1b), ops.i8_encode(Q4, stream=sa, storage=s4b)]
+        if self._use_i8([m1, m4], omega.shape[1]):
+            # K7: both quarter tensors are encoded once (16 int8 residue planes) and serve all 13 thin products; the encoding is
+            # produced by the same library call that builds the tensor (column exponents from the producing kernel's epilogue)
+            def storage(name, shape):
+                nb = ops.i8_encoded_bytes(*shape)
+                return slot.buffer(name, nb, torch.uint8, dev) if slot is not None else torch.empty(nb, dtype=torch.uint8, device=dev)
+            Q1, q1D, e1 = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1], out=o1, enc_storage=storage("enc1", m1))
+            Q4, q4D, e4 = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2], out=o4, enc_storage=storage("enc4", m4))
+            encs = [e1, e4]
+        else:
+            Q1, q1D = self.make_quarter_tensor(st1, k, normalize=False, stream=sa, absmax=mx[0:1], out=o1)
+            Q4, q4D = self.make_quarter_tensor(st4, k + 3, normalize=False, stream=sa, absmax=mx[1:2], out=o4)
         if sa is not stream:
             built = torch.cuda.Event()
             built.record(sa)

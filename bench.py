@@ -519,7 +519,12 @@ def run_b200(args):
         k7 = None
         if use_i8:
             enc = ops.i8_encode(Q)
-            t_enc = timed(lambda: ops.i8_encode(Q, storage=enc.storage))
+            t_enc_alone = timed(lambda: ops.i8_encode(Q, storage=enc.storage))
+            # the encoding as the sweep produces it: inside the quarter-tensor call (column exponents from the K2 epilogue)
+            qa = (st['C'][0], st['E'][0], st['E'][3], st['A'])
+            t_q = timed(lambda: ops.quarter_tensor(*qa, normalize=False, out=Q.view(-1)))
+            t_qe = timed(lambda: ops.quarter_tensor(*qa, normalize=False, out=Q.view(-1), enc_storage=enc.storage))
+            t_enc = t_qe - t_q
             out = torch.empty(m, q, dtype=torch.float64, device=dev)
             t_i8 = timed(lambda: ops.i8_matmul(enc, X, out=out))
             # algorithmic HBM bytes of one K7 product: 16 residue planes of Q (int8) + thin operand in (FP64) + result out (FP64)
@@ -530,6 +535,7 @@ def run_b200(args):
                   "ms": t_i8 * 1e3, "fp64_equivalent_tflops": thin_flops / t_i8 * 1e-12, "x_fp64_dmma_peak": thin_flops / t_i8 * 1e-12 / peak,
                   "int8_tops": 16.0 * 2.0 * m * m * (((q + 15) // 16) * 16) / t_i8 * 1e-12,
                   "encode_ms_per_quarter_tensor": t_enc * 1e3, "encode_gbs": (8.0 + 16.0) * m * m / t_enc * 1e-9,
+                  "encode_ms_standalone_i8_encode": t_enc_alone * 1e3, "quarter_tensor_ms": t_q * 1e3, "quarter_tensor_with_encoding_ms": t_qe * 1e3,
                   "launches_per_step": 13 * site_moves // n, "share_of_step": ((13 * t_i8 + 2 * t_enc) * site_moves / n) / step_s}
             thin["speedup_k7_over_dmma"] = t_thin_dmma / t_i8
             del enc, out

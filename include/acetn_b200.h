@@ -70,6 +70,15 @@ int acetn_b200_quarter_tensor(const double* C, const double* E2, const double* E
                               int64_t D, int64_t d, int normalize, double* Q, double* absmax_out, void* ws, size_t ws_bytes,
                               void* stream);
 
+/* Quarter tensor + its K7 residue encoding in one call (see "K7" below): Q is left un-normalised (absmax_out carries max|Q|, which
+ * acetn_b200_projectors_from_usv applies to the projectors), enc_storage (acetn_b200_i8_encoded_bytes(chi_c D^2, chi_e D^2) bytes)
+ * receives the same encoding acetn_b200_i8_encode(Q) would produce.  For D = 8, d = 2 the producing kernel's epilogue delivers the
+ * column exponents, so the encoding costs ONE pass over the 2 GiB tensor (8 B/element read + 16 B/element written). */
+int acetn_b200_quarter_tensor_enc(const double* C, const double* E2, const double* E1, const double* A,
+                                  const int64_t* a_strides, int64_t chi_a, int64_t chi_b, int64_t chi_c, int64_t chi_e,
+                                  int64_t D, int64_t d, double* Q, double* absmax_out, void* enc_storage, size_t enc_bytes,
+                                  void* ws, size_t ws_bytes, void* stream);
+
 /* ---- randomized SVD family: acetn/linalg/{svd_lowrank,fused_matmul_svd_lowrank,fused_3matmul_svd_lowrank}.py
  *   rSVD of the product M_0 M_1 ... M_{nmat-1} (nmat = 1, 2 or 4) without forming it.  mats[i] is rows[i] x cols[i]
  *   row-major contiguous; Omega is (cols[nmat-1] x q), drawn by the caller with torch.randn exactly as the reference
@@ -154,14 +163,16 @@ int acetn_b200_double_layer(const double* X, int64_t n0, int64_t n1, int64_t in_
                             int64_t d, double* Y, int64_t out_s0, int64_t out_s1, const int64_t* out_es, void* ws,
                             size_t ws_bytes, void* stream);
 
-/* ---- K7: FP64-exact "big x thin" products on the INT8 tensor cores (tcgen05.mma kind::i8 + TMEM + TMA) --------------
+/* ---- K7: FP64-accurate (normwise, P-bit fixed point per row/column scale) "big x thin" products on the INT8 tensor cores (tcgen05.mma kind::i8 + TMEM + TMA) --------------
  *   The thin products of the rSVD chain and of the projector formation (fused_matmul_svd_lowrank.py:33-46,
  *   projectors.py:166-172; `A @ (B @ omega)` etc. in the reference) multiply the same quarter tensors 13 times per
  *   site-move.  i8_encode turns a matrix Q (rows x cols) once into 16 planes of int8 residues (two-sided power-of-two
- *   scaling to 54-bit integers, then mod 16 coprime moduli <= 256); i8_matmul evaluates  out = Q Y  (adjoint = 0, Y: cols x q)
- *   or  out = Q^T Y  (adjoint = 1, Y: rows x q) exactly in integer arithmetic (one INT8 tensor-core GEMM per modulus,
- *   Chinese-remainder reconstruction in 128-bit integers) -- the only rounding is the 2^-54 scaling of the operands, so the
- *   result carries FP64-level error (acetn_b200/csrc/i8crt.cu).  q <= 272; 128 <= rows, cols <= 65535.
+ *   scaling to P-bit integers, P = 54 up to a contraction length of 16384, then mod 16 coprime moduli <= 256); i8_matmul evaluates
+ *   out = Q Y  (adjoint = 0, Y: cols x q)  or  out = Q^T Y  (adjoint = 1, Y: rows x q)  in integer arithmetic (one INT8
+ *   tensor-core GEMM per modulus, Chinese-remainder reconstruction in 128-bit integers): the product of the ROUNDED operands is
+ *   exact; the only rounding is the fixed-point conversion of the operands, 2^-P relative to each entry's row x column scale.  The
+ *   result is therefore NORMWISE FP64-accurate (per row / column scale), not componentwise: entries more than 2^-P below their
+ *   row-and-column maximum are flushed (acetn_b200/csrc/i8crt.cu).  q <= 272; 128 <= rows, cols <= 65535.
  *   storage (device, acetn_b200_i8_encoded_bytes) is caller-owned and opaque. */
 int acetn_b200_i8_supported(int64_t rows, int64_t cols, int64_t q);
 size_t acetn_b200_i8_encoded_bytes(int64_t rows, int64_t cols);

@@ -61,7 +61,7 @@ def gemm_ex(M, N, K, batch, A, B, C, idx, alpha=1.0, beta=0.0, force_tile=0, for
     return C
 
 
-def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, out=None):
+def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, out=None, enc_storage=None):
     t = torch.einsum("ab,bcuU->acuU", C, E2)
     t = torch.einsum("acuU,ealL->cuUelL", t, E1)
     t = torch.einsum("cuUelL,LURDP->cuelRDP", t, A_view)

@@ -174,3 +174,40 @@ def test_i8_engine_matches_dmma_engine(D, chi):
             sa = torch.linalg.svdvals(out["dmma"][1][(1, y)]['C'][k].cpu())
             sb = torch.linalg.svdvals(out["i8"][1][(1, y)]['C'][k].cpu())
             assert float((sa / sa[0] - sb / sb[0]).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("D,chi,d", [(8, 32, 2), (8, 20, 2), (6, 16, 2), (4, 12, 2)])
+def test_quarter_tensor_enc_equals_separate_encoding(D, chi, d):
+    """acetn_b200_quarter_tensor_enc (quarter tensor + K7 encoding in one call; for D = 8, d = 2 the column exponents come from the
+    producing kernel's epilogue) must give bit for bit the storage of acetn_b200_i8_encode applied to the same tensor: residue
+    planes, row and column exponents.  Ragged chi legs and an exactly-zero edge slice included."""
+    cell = orc.random_cell(2, 2, D, chi, d, seed=11)
+    st = cell[(0, 0)]
+    C, E2, E1 = st.C[0].cuda(), st.E[0][:, :chi - 1].contiguous().cuda(), st.E[3][:chi - 2].contiguous().cuda()
+    E2[:, 3] = 0.0                                   # a block of exactly-zero rows of Q
+    E1[5] = 0.0                                      # a block of exactly-zero columns of Q
+    A = st.bond_permute(0).cuda()
+    rows, cols = (chi - 1) * D * D, (chi - 2) * D * D
+    nb = ops.i8_encoded_bytes(rows, cols)
+    s_fused = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    Q, _, enc = ops.quarter_tensor(C, E2, E1, A, normalize=False, enc_storage=s_fused)
+    assert (enc.rows, enc.cols) == (rows, cols) and tuple(Q.shape) == (rows, cols)
+    Qref, _ = ops.quarter_tensor(C, E2, E1, A, normalize=False)
+    assert torch.equal(Q, Qref)
+    s_sep = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    ops.i8_encode(Qref, storage=s_sep)
+    ld = (cols + 127) // 128 * 128
+    planes = 16 * rows * ld
+    a = s_fused[:planes].view(16, rows, ld)[:, :, :cols]
+    b = s_sep[:planes].view(16, rows, ld)[:, :, :cols]
+    assert torch.equal(a, b)
+    off = (planes + 255) // 256 * 256
+    rexp = lambda s: s[off:off + 4 * rows].view(torch.int32)                                  # noqa: E731
+    cexp = lambda s: s[off + (4 * rows + 255) // 256 * 256:][:4 * cols].view(torch.int32)      # noqa: E731
+    assert torch.equal(rexp(s_fused), rexp(s_sep)) and torch.equal(cexp(s_fused), cexp(s_sep))
+    # and the products agree with FP64
+    Y = _rand((cols, 10), 3)
+    ref = Qref @ Y
+    out = ops.i8_matmul(enc, Y)
+    scale = ref.abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
+    assert float(((out - ref).abs() / scale).max()) < 1e-13
