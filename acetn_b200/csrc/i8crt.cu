@@ -41,6 +41,8 @@ __constant__ uint32_t c_p256lo[I8_NMOD] = CRT_P256_LO_INIT;
 __constant__ uint32_t c_p256hi[I8_NMOD] = CRT_P256_HI_INIT;
 __constant__ int c_off0[I8_NMOD] = CRT_OFF0_INIT;
 __constant__ int c_off1[I8_NMOD] = CRT_OFF1_INIT;
+__constant__ int c_off55[I8_NMOD] = CRT_OFF55_INIT;
+__constant__ int c_negmod[I8_NMOD] = CRT_NEGMOD_INIT;
 __constant__ uint32_t c_magic[I8_NMOD] = CRT_MAGIC_INIT;
 __constant__ unsigned long long c_wlo[I8_NMOD] = CRT_W_LO_INIT;
 __constant__ unsigned long long c_whi[I8_NMOD] = CRT_W_HI_INIT;
@@ -90,6 +92,22 @@ __device__ __forceinline__ void residues16u(long long v, int r[I8_NMOD]) {
     }
 }
 
+// The same through v + 2^55 >= 0 (|v| <= 2^55): no sign case (the -2^55 mod m is folded into the accumulator start), and the
+// residue is packed straight into byte `pos` of the plane word -- 5 instructions per residue (2 dp4a, mulhi, mul-sub, insert).
+template <int POS>
+__device__ __forceinline__ void residues16_pack(long long v, uint32_t w[I8_NMOD]) {
+    const unsigned long long u = (unsigned long long)(v + (1LL << 55));
+    const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+#pragma unroll
+    for (int l = 0; l < I8_NMOD; l++) {
+        int s = dp4a_us(hi, c_p256hi[l], c_off55[l]);
+        s = dp4a_us(lo, c_p256lo[l], s);
+        const uint32_t r = __umulhi((uint32_t)s, c_magic[l]) * (uint32_t)c_negmod[l] + (uint32_t)s;      // s - floor(s / m) m: one IMAD
+        if (POS == 0) w[l] = r;                                                        // r < 256: the upper bytes start as zero
+        else asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w[l]) : "r"(r), "r"(1u << (8 * POS)));   // disjoint bytes: add == insert
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // encode: exponents
 // ---------------------------------------------------------------------------------------------------------------------
@@ -111,15 +129,60 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// encode: one CTA per row of the big matrix.  Pass A reads the row once from HBM and finds its exponent after the column
-// scaling, r_i = max_j (exponent(Q_ij) - c_j) <= 0; pass B re-reads it (128 KB: an L2 hit) and writes the 16 residue planes.
-// One HBM pass over Q (8 B/element read + 16 B/element written) instead of three.  Thread = 8 consecutive columns per step.
+// encode: residues of the big matrix in two passes over Q (three before the column exponents came from the producer):
+//   row_exp_kernel   : r_i = max_j (exponent(Q_ij) - c_j) <= 0, one CTA per row (HBM bound, 8 B/element)
+//   encode_big_kernel: thread = 8 consecutive columns of one row -> 16 eight-byte stores, one per plane (issue bound)
+// A fused single-pass variant (persistent CTA per row, second read of the row from L2) was measured slower (2.25 - 2.34 ms against
+// 0.4 + 1.6 ms at 16384^2): with one row per CTA the exponent pass and the residue pass serialise inside the CTA.
 // ---------------------------------------------------------------------------------------------------------------------
-// residues of 8 consecutive columns of one row -> 16 eight-byte stores (one per plane).  Deliberately NOT inlined: as straight-line
-// code it needs 64 registers (the moduli tables stay constant-bank operands); inlined into the row loop the compiler hoists the 80
-// table entries into registers and spills.
-__device__ __noinline__ void encode_chunk8(const double* __restrict__ row, const int32_t* __restrict__ colexp, int64_t j0, int64_t cols,
-                                           int re, int P, int8_t* __restrict__ dst, int64_t plane, int vec_ok) {
+__global__ void __launch_bounds__(256) row_exp_kernel(const double* __restrict__ Q, int64_t cols, int64_t ldq, const int32_t* __restrict__ colexp,
+                                                      int32_t* __restrict__ rowexp, int vec_ok) {
+    const double* row = Q + (int64_t)blockIdx.x * ldq;
+    int mx = EXP_NONE;
+    if (vec_ok) {
+        for (int64_t j0 = (int64_t)threadIdx.x * 2; j0 < cols; j0 += 2048) {
+            double2 t[4];
+            int2 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t j = j0 + 512 * u;
+                if (j + 2 <= cols) {
+                    t[u] = __ldg(reinterpret_cast<const double2*>(row + j));
+                    c[u] = __ldg(reinterpret_cast<const int2*>(colexp + j));
+                } else {
+                    t[u].x = j < cols ? row[j] : 0.0; t[u].y = 0.0;
+                    c[u].x = j < cols ? colexp[j] : 0; c[u].y = 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e0 = exp_field(t[u].x), e1 = exp_field(t[u].y);
+                if (e0) mx = max(mx, e0 - 1022 - c[u].x);
+                if (e1) mx = max(mx, e1 - 1022 - c[u].y);
+            }
+        }
+    } else {
+        for (int64_t j = threadIdx.x; j < cols; j += 256) { int e = exp_field(row[j]); if (e) mx = max(mx, e - 1022 - colexp[j]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ int sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) mx = max(mx, sm[w]);
+        rowexp[blockIdx.x] = mx;                              // EXP_NONE for an all-zero row
+    }
+}
+
+__global__ void __launch_bounds__(256) encode_big_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
+                                                         const int32_t* __restrict__ rowexp, const int32_t* __restrict__ colexp, int P,
+                                                         int8_t* __restrict__ res, int64_t ld, int vec_ok) {
+    const int64_t i = blockIdx.y;
+    const int64_t j0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (j0 >= ld) return;
+    const int re = rowexp[i];
+    const double* row = Q + i * ldq;
     double x[8];
     int ce[8];
     if (vec_ok && j0 + 8 <= cols) {
@@ -138,64 +201,15 @@ __device__ __noinline__ void encode_chunk8(const double* __restrict__ row, const
         }
     }
     uint32_t w0[I8_NMOD], w1[I8_NMOD];
+    long long v[8];
 #pragma unroll
-    for (int l = 0; l < I8_NMOD; l++) { w0[l] = 0; w1[l] = 0; }
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        long long v = 0;
-        if (re > EXP_NONE && ce[c] > EXP_NONE) v = scaled_int(x[c], P - re - ce[c]);
-        int r[I8_NMOD];
-        residues16u(v, r);
-#pragma unroll
-        for (int l = 0; l < I8_NMOD; l++) {
-            // residues of different columns occupy different bytes: a multiply-add packs them (one IMAD instead of SHF + LOP3)
-            if (c < 4) w0[l] += (uint32_t)r[l] * (1u << (8 * (c & 3)));
-            else w1[l] += (uint32_t)r[l] * (1u << (8 * (c & 3)));
-        }
-    }
-#pragma unroll
-    for (int l = 0; l < I8_NMOD; l++) __stcs(reinterpret_cast<uint2*>(dst + l * plane), make_uint2(w0[l], w1[l]));
-}
-
-__global__ void __launch_bounds__(256, 3) encode_rows_kernel(const double* __restrict__ Q, int64_t rows, int64_t cols, int64_t ldq,
-                                                             int32_t* __restrict__ rowexp, const int32_t* __restrict__ colexp, int P,
-                                                             int8_t* __restrict__ res, int64_t ld, int vec_ok) {
-    const int64_t i = blockIdx.x;
-    const double* row = Q + i * ldq;
-    __shared__ int sm[8];
-    // ---- pass A
-    int mx = EXP_NONE;
-    if (vec_ok) {
-#pragma unroll 2
-        for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < cols; j0 += 1024) {
-            if (j0 + 4 <= cols) {
-                const double2 t0 = __ldg(reinterpret_cast<const double2*>(row + j0)), t1 = __ldg(reinterpret_cast<const double2*>(row + j0 + 2));
-                const int4 c = __ldg(reinterpret_cast<const int4*>(colexp + j0));
-                int e0 = exp_field(t0.x), e1 = exp_field(t0.y), e2 = exp_field(t1.x), e3 = exp_field(t1.y);
-                if (e0) mx = max(mx, e0 - 1022 - c.x);
-                if (e1) mx = max(mx, e1 - 1022 - c.y);
-                if (e2) mx = max(mx, e2 - 1022 - c.z);
-                if (e3) mx = max(mx, e3 - 1022 - c.w);
-            } else {
-                for (int64_t j = j0; j < cols; j++) { int e = exp_field(row[j]); if (e) mx = max(mx, e - 1022 - colexp[j]); }
-            }
-        }
-    } else {
-        for (int64_t j = threadIdx.x; j < cols; j += 256) { int e = exp_field(row[j]); if (e) mx = max(mx, e - 1022 - colexp[j]); }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = sm[0];
-#pragma unroll
-    for (int w = 1; w < 8; w++) mx = max(mx, sm[w]);
-    const int re = mx;                                        // EXP_NONE for an all-zero row
-    if (threadIdx.x == 0) rowexp[i] = re;
-    // ---- pass B
+    for (int c = 0; c < 8; c++) v[c] = (re > EXP_NONE && ce[c] > EXP_NONE) ? scaled_int(x[c], P - re - ce[c]) : 0;
+    residues16_pack<0>(v[0], w0); residues16_pack<1>(v[1], w0); residues16_pack<2>(v[2], w0); residues16_pack<3>(v[3], w0);
+    residues16_pack<0>(v[4], w1); residues16_pack<1>(v[5], w1); residues16_pack<2>(v[6], w1); residues16_pack<3>(v[7], w1);
     const int64_t plane = rows * ld;
-#pragma unroll 1
-    for (int64_t j0 = (int64_t)threadIdx.x * 8; j0 < ld; j0 += 2048) encode_chunk8(row, colexp, j0, cols, re, P, res + i * ld + j0, plane, vec_ok);
+#pragma unroll
+    for (int l = 0; l < I8_NMOD; l++)
+        __stcs(reinterpret_cast<uint2*>(res + l * plane + i * ld + j0), make_uint2(w0[l], w1[l]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -599,15 +613,9 @@ int i8_encode_launch(const double* Q, int64_t rows, int64_t cols, int64_t ldq, v
         AB_LAUNCHED();
     }
     const int vec_ok = (ldq % 2 == 0) && (((uintptr_t)Q & 15) == 0) && (((uintptr_t)colexp & 15) == 0);
-    // pass B of a row must find the row in L2: bound the rows in flight (CTAs per SM x SMs x 8 B x cols) to about half of the 126 MB
-    // L2 by padding the dynamic shared memory request (ACETN_B200_I8_ENC_CTAS overrides the CTAs per SM: dev tools only)
-    static const int ctas_env = env_int("ACETN_B200_I8_ENC_CTAS");
-    int per_sm = ctas_env > 0 ? ctas_env : (int)((size_t)(60 << 20) / ((size_t)device_sm_count() * 8 * (size_t)cols));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    const size_t pad_smem = per_sm >= 8 ? 0 : (size_t)(220 * 1024) / per_sm - 1024;
-    AB_ENSURE_SMEM(encode_rows_kernel, 220 * 1024);
-    encode_rows_kernel<<<(unsigned)rows, 256, pad_smem, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld, vec_ok);
+    row_exp_kernel<<<(unsigned)rows, 256, 0, s>>>(Q, cols, ldq, colexp, rowexp, vec_ok);
+    AB_LAUNCHED();
+    encode_big_kernel<<<dim3((unsigned)((ld / 8 + 255) / 256), (unsigned)rows), 256, 0, s>>>(Q, rows, cols, ldq, rowexp, colexp, P, res, ld, vec_ok);
     AB_LAUNCHED();
     enc->res = res; enc->rowexp = rowexp; enc->colexp = colexp; enc->rows = rows; enc->cols = cols; enc->ld = ld; enc->P = P;
     return OK;
