@@ -50,6 +50,17 @@ def release_workspace():
     _workspaces.clear()
 
 
+def workspace_high_water(dev):
+    """Largest scratch buffer this process has needed on `dev` so far (bytes)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return max([b.numel() for k, b in _workspaces.items() if b is not None and k[1] == idx] + [0])
+
+
+def reserve_workspace(dev, stream, nbytes):
+    """Make sure the scratch buffer of (dev, stream) holds nbytes: CUDA-graph capture must not meet the grow path (which synchronises)."""
+    return _ws(dev, nbytes, stream)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
@@ -177,7 +188,7 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     return S, Wt, Jt, info
 
 
-def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False, encs=None):
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False, encs=None, info=None):
     """Randomized SVD of mats[0] @ ... @ mats[-1] with the caller's test matrix omega (n, q).
     Returns U (m,q), S (q), V (n,q), info (int32[2] on device: [kept, jacobi sweeps]).
     want_atq=True additionally returns (AtQ, Wt) = (mats[0]^T Q, core left vectors as rows) and want_u=False skips U
@@ -202,7 +213,8 @@ def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, str
     V = torch.empty(n, q, dtype=torch.float64, device=dev)
     AtQ = torch.empty(cols[0], q, dtype=torch.float64, device=dev) if want_atq else None
     Wt = torch.empty(q, q, dtype=torch.float64, device=dev) if want_atq else None
-    info = torch.empty(2, dtype=torch.int32, device=dev)      # written by the library (no torch kernel on another stream)
+    if info is None:
+        info = torch.empty(2, dtype=torch.int32, device=dev)      # written by the library (no torch kernel on another stream)
     r_arr, c_arr = _lib.i64_array(rows), _lib.i64_array(cols)
     use = (ctypes.c_int32 * nmat)(*[1 if e is not None else 0 for e in encs])
     nb = lib.acetn_b200_rsvd_enc_workspace_bytes(nmat, r_arr, c_arr, q, use)

@@ -141,7 +141,7 @@ class ProjectorCalculator:
         return self._full_rank_projectors(R1, R2, F, d1, d4, ipeps.dims["chi"])
 
     # ---- phase 1 ------------------------------------------------------------------------------------------------
-    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None, slot=None):
+    def begin_half_system(self, ipeps, sites, k, stream=None, omega=None, bulk=None, slot=None, info=None):
         """projectors.py:138-161 : Q1, Q4, rSVD of Q1 @ Q4 (never formed).
         bulk: optional second CUDA stream for the throughput-bound first stage (quarter tensors + their K7 encodings); the rSVD
         chain (K7 products interleaved with ~500 latency-bound TSQR / Jacobi launches) then runs on `stream`, ordered behind
@@ -183,7 +183,7 @@ class ProjectorCalculator:
             stream.wait_event(built)
         # U is never materialised: proj1 = Q1^T U = (Q1^T Qy) U_B reuses the first product of the final adjoint pass
         _, S, V, info, AtQ, Wt = ops.rsvd([Q1, Q4], omega, niter=self.rsvd_niter, reorth_adjoint=False, chi=chi,
-                                          cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True, encs=encs)
+                                          cutoff=self.svd_cutoff, stream=stream, want_u=False, want_atq=True, encs=encs, info=info)
         return {"kind": "half", "mx": mx, "Q1": Q1, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": None, "S": S, "V": V, "info": info,
                 "AtQ": AtQ, "Wt": Wt, "omega": omega, "stream": stream, "encs": encs}
 
@@ -207,6 +207,15 @@ class ProjectorCalculator:
                                  cutoff=self.svd_cutoff, stream=stream, encs=encs)
         return {"kind": "full", "Q1": Q1, "Q2": Q2, "Q3": Q3, "Q4": Q4, "q1D": q1D, "q4D": q4D, "U": U, "S": S, "V": V,
                 "info": info, "omega": omega, "stream": stream, "encs": encs}
+
+    def draw_omega_shape(self, ipeps, sites, k):
+        """An uninitialised tensor with the shape / dtype / device of draw_omega's result (no random draw)."""
+        chi, D = ipeps.dims["chi"], ipeps.dims["bond"]
+        st1, st4 = ipeps[sites[0]], ipeps[sites[3]]
+        m = st1['E'][(0 + k) % 4].shape[1] * D * D
+        n = st4['E'][(3 + k + 3) % 4].shape[0] * D * D
+        A = st1['A']
+        return torch.empty(n, min(chi + self.rsvd_oversampling, m, n), dtype=A.dtype, device=A.device)
 
     def draw_omega(self, ipeps, sites, k):
         """The Gaussian test matrix of this projector, drawn exactly where/how the reference draws it
@@ -266,6 +275,15 @@ class ProjectorCalculator:
             pend["ready"].record(stream)       # the projector pair is complete on the side stream
         return p1.view(*q1D[3:], keep), p2.view(*q4D[:3], keep)
 
+    def finish_static(self, pend, keep):
+        """finish() for a CAPTURED move (half-system rSVD only): the truncated rank is not read back -- the projector pair is formed
+        for the rank `keep` the eager run of the same move produced, and the caller compares info[0] with it after the replay."""
+        mx, encs = pend["mx"], pend.get("encs")
+        p1, p2 = ops.projectors_from_usv(pend["Q1"], pend["Q4"], None, pend["V"], pend["S"], keep, stream=pend["stream"],
+                                         qmax1=mx[0:1], qmax4=mx[1:2], AtQ=pend["AtQ"], Wt=pend["Wt"],
+                                         enc4=encs[1] if encs is not None else None)
+        return p1.view(*pend["q1D"][3:], keep), p2.view(*pend["q4D"][:3], keep)
+
     def calculate_half_system(self, ipeps, sites, k):
         """projectors.py:138-174."""
         return self.finish(self.begin_half_system(ipeps, sites, k))
@@ -296,6 +314,178 @@ class TaskSlot:
         return buf
 
 
+class _ArenaSite:
+    """Fixed-address copies of one site's tensors (what captured moves read and, through `commit`, write).  One per site and
+    mover, shared by all captured phases, so that in steady state nothing is copied between phases: the site's C / E list items
+    ARE these tensors, and `A` is re-copied only when the caller replaced it (a bond update of `evolve`)."""
+
+    def __init__(self, st):
+        self.A = st['A'].detach().clone()
+        self.C = [c.detach().clone().contiguous() for c in st['C']]
+        self.E = [e.detach().clone().contiguous() for e in st['E']]
+        self._a_seen = None
+
+    def __getitem__(self, key):
+        return {'A': self.A, 'C': self.C, 'E': self.E}[key]
+
+    def bond_permute(self, k):
+        return self.A.permute([(i + k) % 4 for i in range(4)] + [4])
+
+    def matches(self, st):
+        return st['A'].shape == self.A.shape and all(st['C'][k].shape == self.C[k].shape and st['E'][k].shape == self.E[k].shape
+                                                     for k in range(4))
+
+    def adopt(self, st):
+        """Make the arena hold the site's current tensors, and the site's C / E list items BE the arena tensors."""
+        a = st['A']
+        seen = (a.data_ptr(), a._version, tuple(a.stride()))
+        if seen != self._a_seen:
+            self.A.copy_(a)
+            self._a_seen = seen
+        for k in range(4):
+            for name, mine in (('C', self.C), ('E', self.E)):
+                cur = st[name][k]
+                if cur.data_ptr() != mine[k].data_ptr():
+                    mine[k].copy_(cur)
+                    st[name][k] = mine[k]
+
+
+class MoveGraph:
+    """One phase (a directional move, or a left+right / up+down pair) captured as a CUDA graph, for the launch-bound regime
+    (BASELINE configs 1-2: a site-move at D=2, chi=20 is ~140 dependent launches of a few microseconds each; SURVEY.md 7 hard
+    part 6, 8f-3).  Built only after an eager run of the same phase left every tensor it touches saturated (chi legs == chi)
+    and every projector at full rank, so all shapes are static:
+
+      * the site / boundary tensors of the lines involved live in an arena of fixed-address buffers; tensors the caller
+        replaced since the last run (e.g. `A` after a bond update) are copied in before the replay;
+      * Omega is drawn OUTSIDE the graph with the same torch.randn calls, in the same order, as the eager path;
+      * the graph holds every kernel of the phase: quarter tensors, rSVD chains, projector GEMMs for the expected rank,
+        absorptions into staging tensors -- no host interaction;
+      * after the replay ONE host read checks that every projector came out with the expected rank (the eager path reads
+        once per projector, projectors.py:164); then the staged C, C, E are committed into the arena (whose tensors ARE the
+        ipeps list items).  If a rank differs the replay is discarded -- nothing was committed -- and the phase re-runs eagerly.
+    Same kernels, launch parameters and order per tensor as the eager single-stream schedule: bit-identical results."""
+
+    def __init__(self, mover, ipeps, groups):
+        self.mover, self.groups = mover, groups
+        self.tasks = [t for g in groups for t in g]
+        pc = mover.projector_calculator
+        self.chi = ipeps.dims["chi"]
+        sites = []
+        for t in self.tasks:
+            for s in [t["s1"], t["s2"]] + list(t["plaq"]):
+                if tuple(s) not in sites:
+                    sites.append(tuple(s))
+        self.sites = sites
+        self.arena = {s: mover.arena_site(ipeps, s) for s in sites}
+        for s in sites:
+            self.arena[s].adopt(ipeps[s])
+        dev = self.arena[sites[0]].A.device
+        self.device = dev
+        view = _ArenaCell(ipeps, self.arena)
+        self.omega = [torch.empty_like(pc.draw_omega_shape(view, t["plaq"], t["k"])) for t in self.tasks]
+        self.infos = torch.zeros(len(self.tasks), 2, dtype=torch.int32, device=dev)
+        self.stream = mover.graph_stream(dev)
+        ops.reserve_workspace(dev, self.stream, ops.workspace_high_water(dev))
+        self.graph = torch.cuda.CUDAGraph()
+        # garbage that owns CUDA resources (a dropped mover's graphs, streams) must not be finalised in the middle of the capture:
+        # freeing device memory / destroying a graph is not allowed while a stream of this thread captures
+        import gc
+        gc.collect()
+        # warm-up on the capture stream (results discarded): grows the scratch buffer to what this single-stream order of the phase
+        # needs and makes every kernel resident, neither of which may happen inside a capture
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            self._enqueue(view)
+        torch.cuda.synchronize(dev)
+        self._keep = None
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                self.staged = self._enqueue(view)
+        finally:
+            gc.enable()
+        self._keep = None            # capture is over: the graph's private pool keeps the addresses of the intermediates
+        self.replays = 0
+
+    def _enqueue(self, view):
+        """Every kernel of the phase.  The independent tasks are forked onto side streams and joined again (captured as parallel
+        branches of the graph), like the eager schedule overlaps their latency-bound chains.  All intermediates stay alive until the
+        caller drops `self._keep`: a block freed in mid-capture could be handed to a kernel of a concurrent branch."""
+        mover, pc, chi = self.mover, self.mover.projector_calculator, self.chi
+        main = torch.cuda.current_stream(self.device)
+        side = [st for st in mover._side_streams(self.device) if st is not None] or [main]
+        keep, staged = [], []
+        n = 0
+        for g in self.groups:
+            p1, p2 = {}, {}
+            used = []
+            for t in g:
+                st = side[n % len(side)]
+                if st is not main:
+                    st.wait_stream(main)
+                    used.append(st)
+                with torch.cuda.stream(st):
+                    pend = pc.begin_half_system(view, t["plaq"], t["k"], stream=st if st is not main else None, omega=self.omega[n],
+                                                info=self.infos[n])
+                    p1[t["key"]], p2[t["key"]] = pc.finish_static(pend, chi)
+                keep.append(pend)
+                n += 1
+            for st in used:
+                main.wait_stream(st)
+            used = []
+            for i, t in enumerate(g):
+                k, src = t["k"], view[t["s1"]]
+                st = side[i % len(side)]
+                if st is not main:
+                    st.wait_stream(main)
+                    used.append(st)
+                with torch.cuda.stream(st):
+                    c1 = mover.renormalize_cj1(src['C'][(3 + k) % 4], src['E'][(2 + k) % 4], p1[t["i"]])
+                    c2 = mover.renormalize_cj2(src['C'][k], src['E'][k], p2[t["j"]])
+                    e = mover.renormalize_ej(src['E'][(3 + k) % 4], src.bond_permute(k), p2[t["i"]], p1[t["j"]])
+                staged.append((t["s2"], k, c1, c2, e))
+            for st in used:
+                main.wait_stream(st)
+            keep.append((p1, p2))
+        self._keep = keep
+        return staged
+
+    def usable(self, ipeps):
+        return ipeps.dims["chi"] == self.chi and all(self.mover._arena.get(s) is self.arena[s] and self.arena[s].matches(ipeps[s])
+                                                     for s in self.sites)
+
+    def run(self, ipeps):
+        """Replay; True when the result was committed, False when a projector rank differed (nothing changed)."""
+        pc = self.mover.projector_calculator
+        for s in self.sites:
+            self.arena[s].adopt(ipeps[s])
+        view = _ArenaCell(ipeps, self.arena)
+        for n, t in enumerate(self.tasks):                  # the reference's draws, in the reference's order
+            self.omega[n].copy_(pc.draw_omega(view, t["plaq"], t["k"]))
+        self.graph.replay()
+        if [int(v) for v in self.infos[:, 0].tolist()] != [self.chi] * len(self.tasks):      # the one host read of the phase
+            return False
+        for s2, k, c1, c2, e in self.staged:
+            ar = self.arena[tuple(s2)]
+            ar.C[(3 + k) % 4].copy_(c1)
+            ar.C[k].copy_(c2)
+            ar.E[(3 + k) % 4].copy_(e)
+        self.replays += 1
+        return True
+
+
+class _ArenaCell:
+    """ipeps-like view whose sites are the arena copies (dims / nx / ny from the real object)."""
+
+    def __init__(self, ipeps, arena):
+        self.dims, self.nx, self.ny, self._arena, self._ipeps = ipeps.dims, ipeps.nx, ipeps.ny, arena, ipeps
+
+    def __getitem__(self, site):
+        ar = self._arena.get(tuple(site))
+        return ar if ar is not None else self._ipeps[site]
+
+
 class DirectionalMover:
     """acetn/renormalization/directional_mover.py:5-366 (non-distributed moves).
 
@@ -317,6 +507,10 @@ class DirectionalMover:
         self.stagger = os.environ.get("ACETN_B200_STAGGER", "1") != "0"
         # at most this many projector tasks are begun-but-unfinished at any time (each holds 2 quarter tensors + encodings)
         self.inflight = max(1, int(os.environ.get("ACETN_B200_INFLIGHT", "4")))
+        # CUDA-graph replay of whole phases in the launch-bound regime (MoveGraph): "auto" = quarter tensors below GRAPH_MAX_DIM
+        self.use_graphs = os.environ.get("ACETN_B200_GRAPHS", "auto")
+        self._graphs, self._graph_ok, self._graph_stream, self._arena = {}, {}, None, {}
+        self.graph_replays = 0
         self._slots = []
         self._config = config
         self._sharded = None
@@ -346,8 +540,79 @@ class DirectionalMover:
         return self._bulk_stream, self._hi_streams[:n]
 
     def release(self):
-        """Drop the task-slot buffers (they are re-created on demand)."""
+        """Drop the task-slot buffers and captured graphs (they are re-created on demand)."""
         self._slots = []
+        self._graphs, self._graph_ok, self._arena = {}, {}, {}
+
+    # chi * D^2 up to which a phase is replayed as a CUDA graph ("auto").  Measured (tools/small_config_bench.py, 2x2 cell): D=2 chi=20
+    # (chi D^2 = 80) 134 -> 166 sweeps/s; D=4 chi=64 (1024) 45.5 -> 40.6: there the eager schedule's piecewise absorptions and stream
+    # priorities are worth more than the saved launch overhead -- the dependent-kernel latency, not the launch, bounds both
+    GRAPH_MAX_DIM = 256
+
+    def arena_site(self, ipeps, site):
+        """The fixed-address buffers of `site` (created from its current, saturated tensors; rebuilt when a shape changed, which
+        also drops every captured phase that used the old buffers -- MoveGraph.usable)."""
+        ar = self._arena.get(site)
+        if ar is None or not ar.matches(ipeps[site]):
+            ar = self._arena[site] = _ArenaSite(ipeps[site])
+        return ar
+
+    def graph_stream(self, device):
+        if self._graph_stream is None:
+            self._graph_stream = torch.cuda.Stream(device=device)
+        return self._graph_stream
+
+    def _graph_candidate(self, ipeps, groups):
+        """True when the phase may run as a captured graph: half-system rSVD, launch-bound size, every tensor of the lines involved
+        saturated, source and target line of every move disjoint, no recorder.  (A captured phase reads the pre-phase state
+        throughout and commits afterwards, which equals the eager order because no task reads a slot another task writes.)"""
+        pc = self.projector_calculator
+        if self.use_graphs == "0" or pc.spectra is not None or pc.projectors != "half-system" or pc.svd_type != "rsvd":
+            return False
+        chi, D = ipeps.dims["chi"], ipeps.dims["bond"]
+        if self.use_graphs != "1" and chi * D * D > self.GRAPH_MAX_DIM:
+            return False
+        if min(chi + pc.rsvd_oversampling, chi * D * D) <= chi:          # q must exceed chi for the expected rank to be chi
+            return False
+        tasks = [t for g in groups for t in g]
+        for g in groups:      # per move: source line != target line (across the moves of a pair the tensor SLOTS are disjoint, see move_pair)
+            if not {tuple(t["s1"]) for t in g}.isdisjoint({tuple(t["s2"]) for t in g}):
+                return False
+        for t in tasks:
+            for s in [t["s1"], t["s2"]] + list(t["plaq"]):
+                st = ipeps[s]
+                if st['A'].device.type != "cuda":
+                    return False
+                for k in range(4):
+                    if tuple(st['C'][k].shape) != (chi, chi) or tuple(st['E'][k].shape) != (chi, chi, D, D):
+                        return False
+        return True
+
+    def _run_graphed(self, ipeps, moves):
+        """Replay the phase `moves` from its captured graph when possible.  Returns True when done."""
+        key = tuple(moves)
+        if not self._graph_ok.get(key):
+            return False
+        groups = [self.move_tasks(ipeps, k, line) for k, line in moves]
+        if not self._graph_candidate(ipeps, groups):
+            return False
+        g = self._graphs.get(key)
+        if g is not None and not g.usable(ipeps):
+            g = None
+        if g is None:
+            g = self._graphs[key] = MoveGraph(self, ipeps, groups)
+        if g.run(ipeps):
+            self.graph_replays += 1
+            return True
+        self._graph_ok[key] = False          # a projector lost rank: back to the eager path until a full-rank eager run re-arms it
+        return False
+
+    def _note_eager(self, ipeps, moves, ranks):
+        """After an eager run of a phase: arm the graph path when every projector had full rank chi."""
+        if self.use_graphs == "0":
+            return
+        chi = ipeps.dims["chi"]
+        self._graph_ok[tuple(moves)] = bool(ranks) and all(r == chi for r in ranks)
 
     def _pipeline(self, ipeps, specs, omegas, streams, retired, bulk=None):
         """Generator over the projector tasks specs = [(sites, k)]: yields (n, pending, (proj1, proj2)) in task order while at most
@@ -439,12 +704,15 @@ class DirectionalMover:
         read and write disjoint boundary tensors, which is what the reference's distributed schedule relies on
         (directional_mover.py:183-271); the Omega draws keep the sequential order (first move's sites, then the
         second's)."""
+        if self._run_graphed(ipeps, moves):
+            return
         groups = [self.move_tasks(ipeps, k, line) for k, line in moves]
         tasks = [t for g in groups for t in g]
         if not (self.staggered() and len(groups) > 1):
             p1, p2 = self._projectors_of_tasks(ipeps, tasks)
             for t in tasks:
                 self._absorb_task(ipeps, t, p1, p2)
+            self._note_eager(ipeps, moves, [p.shape[-1] for p in p1.values()])
             return
         # staggered schedule: the moves of the phase touch disjoint boundary tensors (see above), so the absorptions of a move
         # may run -- on their own stream -- while the projectors of the following moves are still being computed
@@ -477,6 +745,7 @@ class DirectionalMover:
         for st in streams + [bulk]:
             main.wait_stream(st)
         del retired                  # per-task tensors are released only after the main stream is ordered behind the side streams
+        self._note_eager(ipeps, moves, [p.shape[-1] for p in p1.values()])
 
     def _finish_and_absorb_piecewise(self, ipeps, g, pipe, p1, p2, bulk):
         """renormalize_boundary (directional_mover.py:293-303) of one move, issued on the bulk stream as soon as its inputs exist:
@@ -570,6 +839,8 @@ class DirectionalMover:
 
     # ---- the four moves (directional_mover.py:23-97) -----------------------------------------------------------
     def left_move(self, ipeps, xi):
+        if self._run_graphed(ipeps, [(0, xi)]):
+            return
         nx, ny = ipeps.nx, ipeps.ny
         plaq = []
         for yi in range(ny):
@@ -580,8 +851,11 @@ class DirectionalMover:
             xj = (xi + 1) % nx
             yj = (yi + 1) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xj, yi), yi, yj, k=0)
+        self._note_eager(ipeps, [(0, xi)], [p.shape[-1] for p in proj1.values()])
 
     def up_move(self, ipeps, yi):
+        if self._run_graphed(ipeps, [(1, yi)]):
+            return
         nx, ny = ipeps.nx, ipeps.ny
         plaq = []
         for xi in range(nx):
@@ -592,8 +866,11 @@ class DirectionalMover:
             xj = (xi + 1) % nx
             yj = (yi - 1 + ny) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xi, yj), xi, xj, k=1)
+        self._note_eager(ipeps, [(1, yi)], [p.shape[-1] for p in proj1.values()])
 
     def right_move(self, ipeps, xi):
+        if self._run_graphed(ipeps, [(2, xi)]):
+            return
         nx, ny = ipeps.nx, ipeps.ny
         plaq = []
         for yi in range(ny):
@@ -604,8 +881,11 @@ class DirectionalMover:
             xj = (xi - 1 + nx) % nx
             yj = (yi - 1 + ny) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xj, yi), yi, yj, k=2)
+        self._note_eager(ipeps, [(2, xi)], [p.shape[-1] for p in proj1.values()])
 
     def down_move(self, ipeps, yi):
+        if self._run_graphed(ipeps, [(3, yi)]):
+            return
         nx, ny = ipeps.nx, ipeps.ny
         plaq = []
         for xi in range(nx):
@@ -616,6 +896,7 @@ class DirectionalMover:
             xj = (xi - 1 + nx) % nx
             yj = (yi + 1) % ny
             self.renormalize_boundary(ipeps, proj1, proj2, (xi, yi), (xi, yj), xi, xj, k=3)
+        self._note_eager(ipeps, [(3, yi)], [p.shape[-1] for p in proj1.values()])
 
     # ---- plaquette pickers (directional_mover.py:99-181) ----------------------------------------------------------
     def calculate_left_projectors(self, ipeps, xi, yi):

@@ -93,7 +93,7 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     return S, Vh.contiguous(), U.t().contiguous(), info
 
 
-def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False, encs=None):
+def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, stream=None, want_u=True, want_atq=False, encs=None, info=None):
     def fwd(Y):
         for M in reversed(mats):
             Y = M @ Y

@@ -313,3 +313,53 @@ def test_staggered_schedule_is_bit_identical(nx, ny, D, chi):
             for k in range(4):
                 assert torch.equal(outs[0][s]['C'][k], other[s]['C'][k])
                 assert torch.equal(outs[0][s]['E'][k], other[s]['E'][k])
+
+
+@pytest.mark.parametrize("nx,ny,D,chi,paired", [(2, 2, 2, 8, True), (2, 2, 3, 12, True), (3, 2, 2, 6, False), (2, 2, 2, 20, False), (2, 2, 4, 16, True)])
+def test_graph_replay_is_bit_identical(nx, ny, D, chi, paired, monkeypatch):
+    """Launch-bound sizes run their phases as captured CUDA graphs once the boundary has saturated (MoveGraph: fixed-address arena,
+    Omega drawn outside the graph in the reference's order, one host read per phase).  Same kernels in the same order: the tensors
+    after several sweeps must equal the eager schedule's bit for bit, and graphs must actually have been replayed."""
+    cell = orc.random_cell(nx, ny, D, chi, 2, seed=13)
+    monkeypatch.setenv("ACETN_B200_PAIR_MOVES", "1" if paired else "0")
+    out = {}
+    for mode in ("0", "auto"):
+        monkeypatch.setenv("ACETN_B200_GRAPHS", mode)
+        torch.manual_seed(5)
+        ip = Ipeps.from_plain(cell, CTMRGConfig(steps=6))
+        mover = DirectionalMover(ip.ctmrg_config)
+        ctmrg(ip, ip.ctmrg_config, mover)
+        torch.cuda.synchronize()
+        out[mode] = (ip, mover.graph_replays)
+    assert out["0"][1] == 0 and out["auto"][1] > 0
+    a, b = out["0"][0], out["auto"][0]
+    for s in a.site_list:
+        for k in range(4):
+            assert torch.equal(a[s]['C'][k], b[s]['C'][k]) and torch.equal(a[s]['E'][k], b[s]['E'][k])
+
+
+def test_graph_replay_follows_replaced_site_tensors(monkeypatch):
+    """`evolve` replaces the site tensor A after every bond update (fast_full_update.py:61-62): a captured phase must pick the new
+    tensor up (arena copy-in) and give the eager result for it."""
+    monkeypatch.setenv("ACETN_B200_PAIR_MOVES", "1")
+    cell = orc.random_cell(2, 2, 2, 8, 2, seed=21)
+    out = {}
+    for mode in ("0", "auto"):
+        monkeypatch.setenv("ACETN_B200_GRAPHS", mode)
+        torch.manual_seed(9)
+        ip = Ipeps.from_plain(cell, CTMRGConfig(steps=4))
+        mover = DirectionalMover(ip.ctmrg_config)
+        ctmrg(ip, ip.ctmrg_config, mover)
+        g = torch.Generator().manual_seed(3)
+        for s in ip.site_list:
+            A = torch.rand(2, 2, 2, 2, 2, dtype=torch.float64, generator=g) - 0.5
+            ip[s]['A'] = (A / A.norm()).cuda()
+        for bond in ip.bond_list:
+            mover.absorb_bond(ip, bond)
+        torch.cuda.synchronize()
+        out[mode] = (ip, mover.graph_replays)
+    assert out["auto"][1] > out["0"][1] == 0
+    for s in out["0"][0].site_list:
+        for k in range(4):
+            assert torch.equal(out["0"][0][s]['C'][k], out["auto"][0][s]['C'][k])
+            assert torch.equal(out["0"][0][s]['E'][k], out["auto"][0][s]['E'][k])
