@@ -190,6 +190,11 @@ class ShardedCtmrg:
         omegas = [cp.draw_omega(ip, t) for t in tasks]                    # every rank replays every draw
         coop = [n for n in range(len(tasks)) if self.owner_group(n) == self.gi]      # tasks my group computes
         if self.G > 1:
+            # the ranks of a group multiply their row blocks by the SAME test matrix: do not rely on equal generator states, take the
+            # group leader's draw (34 MB per task over NVLink)
+            for n in coop:
+                omegas[n] = omegas[n].contiguous()
+                dist.broadcast(omegas[n], src=self.gi * self.G, group=self.pair_group)
             coop_pairs = cp.projectors(ip, [tasks[n] for n in coop], [omegas[n] for n in coop], group=self.pair_group,
                                        group_rank=self.g, group_size=self.G)
         else:

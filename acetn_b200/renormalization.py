@@ -316,14 +316,13 @@ class TaskSlot:
 
 class _ArenaSite:
     """Fixed-address copies of one site's tensors (what captured moves read and, through `commit`, write).  One per site and
-    mover, shared by all captured phases, so that in steady state nothing is copied between phases: the site's C / E list items
-    ARE these tensors, and `A` is re-copied only when the caller replaced it (a bond update of `evolve`)."""
+    mover, shared by all captured phases, so that in steady state no boundary tensor is copied between phases: the site's C / E
+    list items ARE these tensors; only the 64 KiB site tensor `A` is copied in before every replay."""
 
     def __init__(self, st):
         self.A = st['A'].detach().clone()
         self.C = [c.detach().clone().contiguous() for c in st['C']]
         self.E = [e.detach().clone().contiguous() for e in st['E']]
-        self._a_seen = None
 
     def __getitem__(self, key):
         return {'A': self.A, 'C': self.C, 'E': self.E}[key]
@@ -337,11 +336,10 @@ class _ArenaSite:
 
     def adopt(self, st):
         """Make the arena hold the site's current tensors, and the site's C / E list items BE the arena tensors."""
-        a = st['A']
-        seen = (a.data_ptr(), a._version, tuple(a.stride()))
-        if seen != self._a_seen:
-            self.A.copy_(a)
-            self._a_seen = seen
+        # `A` is the caller's object (the reference's setter clones, site_tensor.py:77): it cannot be adopted, and neither its address
+        # (allocator reuse) nor a version counter (inference tensors have none) tells whether a bond update replaced it -> copy, 1 launch
+        if st['A'].data_ptr() != self.A.data_ptr():
+            self.A.copy_(st['A'])
         for k in range(4):
             for name, mine in (('C', self.C), ('E', self.E)):
                 cur = st[name][k]
