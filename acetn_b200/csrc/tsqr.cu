@@ -1,13 +1,22 @@
 // K4: orthonormal basis of a tall-skinny matrix (the QR steps of the randomized SVD, reference
 // acetn/linalg/fused_matmul_svd_lowrank.py:38,43; only the Q factor is ever used there).
 //
-// Block classical Gram-Schmidt with re-orthogonalisation (BCGS2) over 32-column panels; the inter-panel
-// projections are two K1 DGEMMs each, the intra-panel factorisation is a Householder TSQR:
-//   level 0: every 256-row chunk is factored in shared memory (reflectors stay in place, R goes to a stack),
-//   level l: the stack of R factors is factored the same way until one chunk is left,
-//   then the explicit Q is formed top-down by applying the stored reflectors to [M;0] blocks.
-// Householder keeps ||Q^T Q - I|| at machine precision for any conditioning of Y (CholeskyQR would lose the
-// trailing directions of the power-iterated Y, SURVEY.md section 7 hard part 2).
+// Block classical Gram-Schmidt with re-orthogonalisation (BCGS2) over 32-column panels; the inter-panel projections are two K1
+// DGEMMs each.  A panel P (m x b) is orthonormalised in one of two ways, decided ON THE DEVICE (no host read):
+//
+//   fast path, CholeskyQR2:  twice { G = P^T P (partial Gram per 256-row chunk, fixed-order reduction) ; G = R^T R ; P <- P R^-1 }
+//     5 short launches.  Taken only when it is safe: every Cholesky pivot of the first pass must keep more than 1e-11 of its
+//     diagonal entry (cond(P) below ~3e5, so that the second pass restores orthogonality to machine precision), no zero columns.
+//
+//   fallback, Householder TSQR with explicit chunk factors (the only path of round 1, 4x the latency): every 256-row chunk is
+//     factored X = Q0 R0 by Householder reflections and Q0 formed from the reflectors, the stack of R factors is factored the
+//     same way until one chunk is left, then chunk c of level l <- Q0_c * (rows [c b, c b + b) of the final Q of level l + 1).
+//     Keeps ||Q^T Q - I|| at machine precision for ANY conditioning of Y -- the power-iterated Y of converged physical states reaches
+//     cond 1e20 (SURVEY.md section 7 hard part 2), where CholeskyQR would lose the trailing directions; such panels fail the pivot
+//     test and take this path, while well-conditioned panels (the first and last orthonormalisation of a projector, random benchmark
+//     tensors) take the short one.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace ab200 {
@@ -28,14 +37,21 @@ constexpr int TS_NW = TS_CH / 32;
 //   x_c <- x_c - vraw (g * vraw^T x_c),  vraw = (alpha - beta) v,  g = tau / (alpha - beta)^2 = 1 / (nrm (nrm + |alpha|))
 // so nobody has to scale the pivot column inside the loop (the 1/(alpha - beta) factors and the diagonal beta are applied when
 // the reflectors are written out), every warp executes the same ~200 instructions per step, and a step needs two barriers.
-__global__ void __launch_bounds__(TS_CH, 1)
-tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
-                   double* __restrict__ tau_out, const int* __restrict__ run_flag) {
-    if (run_flag != nullptr && *run_flag == 0) return;    // second BCGS pass found the panel already orthogonal to eps
-    __shared__ __align__(16) double col_s[TS_CH];   // raw pivot column of the current step
-    __shared__ double part[TS_NW][TS_PB];           // per-warp partial dots
-    __shared__ double partn[TS_NW];                 // per-warp partial sums of squares of the pivot column below the diagonal
-    __shared__ double tau_s[TS_PB], beta_s[TS_PB], scale_s[TS_PB];
+struct FactorSmem {
+    double col_s[TS_CH];            // raw pivot column of the current step
+    double part[TS_NW][TS_PB];      // per-warp partial dots
+    double partn[TS_NW];            // per-warp partial sums of squares of the pivot column below the diagonal
+    double tau_s[TS_PB], beta_s[TS_PB], scale_s[TS_PB];
+};
+
+__device__ __forceinline__ void tsqr_factor_body(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
+                                                 double* __restrict__ tau_out, FactorSmem& fs) {
+    double (&col_s)[TS_CH] = fs.col_s;
+    double (&part)[TS_NW][TS_PB] = fs.part;
+    double (&partn)[TS_NW] = fs.partn;
+    double (&tau_s)[TS_PB] = fs.tau_s;
+    double (&beta_s)[TS_PB] = fs.beta_s;
+    double (&scale_s)[TS_PB] = fs.scale_s;
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
@@ -140,11 +156,8 @@ tsqr_factor_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, dou
 }
 
 // Form the explicit Q rows of one chunk: Q_chunk = H_0 ... H_{b-1} [M; 0], M = Min rows [chunk*b, chunk*b + b) (identity if null).
-__global__ void __launch_bounds__(TS_CH, 1)
-tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
-                  const double* __restrict__ Min, const int* __restrict__ run_flag) {
-    if (run_flag != nullptr && *run_flag == 0) return;
-    extern __shared__ double sm[];
+__device__ __forceinline__ void tsqr_apply_body(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
+                                                const double* __restrict__ Min, double* sm) {
     constexpr int VP = TS_CH + 2;                  // even pitch: 16-byte aligned rows for LDS.128 reads of the reflectors
     double* Vs = sm;                               // [TS_PB][VP]: reflector j with unit diagonal, zeros above
     double* part = sm + TS_PB * VP;             // [2][TS_NW][TS_PB]
@@ -194,6 +207,218 @@ tsqr_apply_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared pieces.  Thread (warp w, lane c) keeps rows 32w..32w+31 of column c of its 256-row chunk in registers (as in the
+// Householder kernels); the chunk is staged transposed in shared memory, Xt[c][r], so a column's 32 rows are contiguous.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CQ_XP = TS_CH + 2;            // pitch of Xt (even: 16-byte aligned rows for 128-bit broadcast reads)
+constexpr int CQ_GP = TS_PB + 1;            // pitch of the small matrices
+constexpr double CQ_PIVOT_TOL = 1e-11;
+
+__device__ __forceinline__ void chunk_load(double (&x)[32], const double* __restrict__ P, int64_t ld, int64_t r0, int rows, int b, int w, int c) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const int r = 32 * w + i;
+        x[i] = (r < rows && c < b) ? P[(r0 + r) * ld + c] : 0.0;
+    }
+}
+__device__ __forceinline__ void chunk_store(const double (&x)[32], double* __restrict__ P, int64_t ld, int64_t r0, int rows, int b, int w, int c) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const int r = 32 * w + i;
+        if (r < rows && c < b) P[(r0 + r) * ld + c] = x[i];
+    }
+}
+__device__ __forceinline__ void chunk_stage(const double (&x)[32], double* __restrict__ Xt, int w, int c) {
+    double2* dst = reinterpret_cast<double2*>(Xt + c * CQ_XP + 32 * w);
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[i] = make_double2(x[2 * i], x[2 * i + 1]);
+}
+// x[i] (rows 32w+i of column c)  <-  sum_{c' < b} X[row][c'] * M[c'][c]   with X staged in Xt and M (pitch mp) in shared memory
+__device__ __forceinline__ void chunk_times_matrix(double (&x)[32], const double* __restrict__ Xt, const double* __restrict__ M, int mp, int b,
+                                                   int w, int c, bool upper) {
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    const int kmax = upper ? (c < b ? c + 1 : 0) : b;        // upper triangular M: only c' <= c contribute
+    for (int k = 0; k < kmax; k++) {
+        const double m = M[k * mp + c];
+        const double2* src = reinterpret_cast<const double2*>(Xt + k * CQ_XP + 32 * w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const double2 t = src[i];
+            acc[2 * i] = fma(t.x, m, acc[2 * i]);
+            acc[2 * i + 1] = fma(t.y, m, acc[2 * i + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = acc[i];
+}
+// partial Gram matrix of this CTA's chunk -> Gout[32][CQ_GP] (global): G[c][k] = sum_rows X[r][c] X[r][k]
+// (every thread accumulates its column against all b columns over its warp's 32 rows; 8-way reduction through shared memory)
+__device__ __forceinline__ void chunk_gram(const double (&x)[32], const double* __restrict__ Xt, double* __restrict__ part, int b, int w, int c,
+                                           double* __restrict__ Gout) {
+    for (int k = 0; k < b; k += 2) {
+        const double2* s0 = reinterpret_cast<const double2*>(Xt + k * CQ_XP + 32 * w);
+        const double2* s1 = reinterpret_cast<const double2*>(Xt + (k + 1) * CQ_XP + 32 * w);      // k + 1 <= 31: inside Xt (zero column if >= b)
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) p[u] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const double2 t = s0[i], u = s0[i + 1], v = s1[i], z = s1[i + 1];
+            p[0] = fma(t.x, x[2 * i], p[0]); p[1] = fma(t.y, x[2 * i + 1], p[1]);
+            p[2] = fma(u.x, x[2 * i + 2], p[2]); p[3] = fma(u.y, x[2 * i + 3], p[3]);
+            p[4] = fma(v.x, x[2 * i], p[4]); p[5] = fma(v.y, x[2 * i + 1], p[5]);
+            p[6] = fma(z.x, x[2 * i + 2], p[6]); p[7] = fma(z.y, x[2 * i + 3], p[7]);
+        }
+        part[(w * TS_PB + c) * CQ_GP + k] = (p[0] + p[1]) + (p[2] + p[3]);
+        part[(w * TS_PB + c) * CQ_GP + k + 1] = (p[4] + p[5]) + (p[6] + p[7]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TS_PB * TS_PB; e += TS_CH) {
+        const int i = e >> 5, k = e & 31;
+        double g = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < TS_NW; ww++) g += part[(ww * TS_PB + i) * CQ_GP + k];
+        Gout[i * CQ_GP + k] = (i < b && k < b) ? g : 0.0;
+    }
+}
+constexpr size_t CQ_SMEM = (size_t)(TS_PB * CQ_XP + TS_NW * TS_PB * CQ_GP + TS_PB * CQ_GP) * sizeof(double);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path: CholeskyQR2 of the whole panel.  state[0] = 1 while the fast path is valid, state[1] = 1 once the panel is done.
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 0: partial Gram of every chunk.   pass 1: P <- P Rinv (if the first factorisation was accepted), then the partial Gram again.
+// pass 2: P <- P Rinv (if the second one was accepted).
+__global__ void __launch_bounds__(TS_CH, 1)
+cholqr_chunk_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ Rinv, double* __restrict__ Gpart,
+                    const int* __restrict__ state, const int* __restrict__ run_flag, int pass) {
+    if (run_flag != nullptr && *run_flag == 0) return;    // second BCGS pass found the panel already orthogonal to eps
+    if (pass > 0 && state[0] == 0) return;                // the panel went to the Householder path
+    extern __shared__ __align__(16) double sm[];
+    double* Xt = sm;
+    double* part = Xt + TS_PB * CQ_XP;
+    double* Ms = part + TS_NW * TS_PB * CQ_GP;
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
+    double x[32];
+    chunk_load(x, P, ld, r0, rows, b, w, c);
+    if (pass > 0) {
+        for (int e = tid; e < TS_PB * TS_PB; e += TS_CH) Ms[(e >> 5) * CQ_GP + (e & 31)] = Rinv[(e >> 5) * CQ_GP + (e & 31)];
+        chunk_stage(x, Xt, w, c);
+        __syncthreads();
+        chunk_times_matrix(x, Xt, Ms, CQ_GP, b, w, c, true);
+        chunk_store(x, P, ld, r0, rows, b, w, c);
+        if (pass == 2) return;
+        __syncthreads();
+    }
+    chunk_stage(x, Xt, w, c);
+    __syncthreads();
+    chunk_gram(x, Xt, part, b, w, c, Gpart + (int64_t)blockIdx.x * TS_PB * CQ_GP);
+}
+
+// One CTA: G = sum of the partial Gram matrices (fixed order), Cholesky G = R^T R in the registers of warp 0 (lane k = column k; 32
+// fully unrolled steps of shuffles + FMAs), R^-1 by back substitution.  pass 1: the factorisation is accepted only if every pivot
+// keeps more than CQ_PIVOT_TOL of its diagonal entry, otherwise state[0] <- 0 (Householder path).  pass 2: G is I + O(eps cond^2);
+// a failed pivot there also hands the (already better conditioned) panel to the Householder path; success sets state[1].
+__global__ void __launch_bounds__(TS_CH, 1)
+cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, double* __restrict__ Rinv, int* __restrict__ state,
+                     const int* __restrict__ run_flag, int pass) {
+    if (run_flag != nullptr && *run_flag == 0) return;
+    if (pass == 1) { if (threadIdx.x == 0) { state[0] = 1; state[1] = 0; } }
+    else if (state[0] == 0) return;
+    __shared__ double G[TS_PB * CQ_GP];
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
+    for (int e = tid; e < TS_PB * TS_PB; e += TS_CH) {
+        const int i = e >> 5, k = e & 31;
+        double g = 0.0;
+        for (int ch = 0; ch < nchunks; ch++) g += Gpart[(int64_t)ch * TS_PB * CQ_GP + i * CQ_GP + k];
+        G[i * CQ_GP + k] = (i < b && k < b) ? g : (i == k ? 1.0 : 0.0);          // identity padding keeps the unrolled steps regular
+    }
+    __syncthreads();
+    if (w != 0) return;
+    double g[TS_PB], dinv[TS_PB];
+#pragma unroll
+    for (int i = 0; i < TS_PB; i++) g[i] = G[i * CQ_GP + c];
+    const double gdiag = G[c * CQ_GP + c];
+    bool good = true;
+#pragma unroll
+    for (int j = 0; j < TS_PB; j++) {
+        const double d = __shfl_sync(0xffffffffu, g[j], j);                       // current pivot G[j][j]
+        const double d0 = __shfl_sync(0xffffffffu, gdiag, j);                     // its original diagonal entry
+        good = good && (d > CQ_PIVOT_TOL * d0) && (d0 < 1e300);
+        const double inv = d > 0.0 ? rsqrt(d) : 0.0;
+        dinv[j] = inv;                                                            // 1 / R[j][j] (every lane)
+        const double rjk = c >= j ? g[j] * inv : 0.0;                             // R[j][c]
+        g[j] = rjk;
+#pragma unroll
+        for (int i = j + 1; i < TS_PB; i++) g[i] = fma(-__shfl_sync(0xffffffffu, rjk, i), rjk, g[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < TS_PB; i++) G[i * CQ_GP + c] = i <= c ? g[i] : 0.0;       // R (upper)
+    __syncwarp();
+    // R^-1 (upper), column c by back substitution in axpy form (one FMA + one multiply on the critical path per step)
+    double sv[TS_PB];
+#pragma unroll
+    for (int i = 0; i < TS_PB; i++) sv[i] = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = TS_PB - 1; i >= 0; i--) {
+        const double vi = i <= c ? sv[i] * dinv[i] : 0.0;
+        sv[i] = vi;
+#pragma unroll
+        for (int k = 0; k < i; k++) sv[k] = fma(-G[k * CQ_GP + i], vi, sv[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < TS_PB; i++) Rinv[i * CQ_GP + c] = sv[i];
+    if (c == 0) {
+        if (!good) state[0] = 0;
+        else if (pass == 2) state[1] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fallback: Householder factorisation of one chunk + the explicit Q from its reflectors (the two bodies above), one launch per level.
+// Runs only when the fast path gave up (state[0] == 0).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TS_CH, 1)
+tsqr_chunk_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack, double* __restrict__ tau_scratch,
+                  const int* __restrict__ state, const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;
+    if (state != nullptr && state[1] != 0) return;        // CholeskyQR2 finished the panel
+    extern __shared__ __align__(16) double sm[];
+    __shared__ FactorSmem fs;
+    tsqr_factor_body(P, ld, nrows, b, Rstack, tau_scratch, fs);
+    __syncthreads();
+    tsqr_apply_body(P, ld, nrows, b, tau_scratch, nullptr, sm);
+}
+
+// Q chunk c of a level  <-  Q0_c * M_c,  M_c = rows [c b, c b + b) of the final explicit Q of the next level (ld = b)
+__global__ void __launch_bounds__(TS_CH, 1)
+tsqr_mul_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ Mnext, const int* __restrict__ state,
+                const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;
+    if (state != nullptr && state[1] != 0) return;
+    extern __shared__ __align__(16) double sm[];
+    double* Xt = sm;
+    double* Ms = sm + TS_PB * CQ_XP;                  // [TS_PB][CQ_GP]
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
+    double x[32];
+    chunk_load(x, P, ld, r0, rows, b, w, c);
+    chunk_stage(x, Xt, w, c);
+    for (int e = tid; e < TS_PB * TS_PB; e += TS_CH) {
+        const int i = e >> 5, k = e & 31;
+        Ms[i * CQ_GP + k] = (i < b && k < b) ? Mnext[((int64_t)blockIdx.x * b + i) * b + k] : 0.0;
+    }
+    __syncthreads();
+    chunk_times_matrix(x, Xt, Ms, CQ_GP, b, w, c, false);
+    chunk_store(x, P, ld, r0, rows, b, w, c);
+}
+constexpr size_t MUL_SMEM = (size_t)(TS_PB * CQ_XP + TS_PB * CQ_GP) * sizeof(double);
+
 // run_flag = 1 iff max|c| > thresh: the re-orthogonalisation coefficients of the second BCGS pass are not negligible
 __global__ void bcgs_flag_kernel(const double* __restrict__ c, int n, double thresh, int* __restrict__ run_flag) {
     __shared__ int any;
@@ -207,7 +432,6 @@ __global__ void bcgs_flag_kernel(const double* __restrict__ c, int n, double thr
 }
 
 namespace {
-constexpr size_t FACTOR_SMEM = 0;
 constexpr size_t APPLY_SMEM = (size_t)(TS_PB * (TS_CH + 2) + 2 * TS_NW * TS_PB + TS_PB) * sizeof(double);
 
 struct Levels {
@@ -230,12 +454,18 @@ size_t tsqr_scratch_doubles(int64_t m) {
     Levels L = plan_levels(m, TS_PB);
     size_t tot = 0;
     for (int l = 0; l < L.n; l++) tot += (size_t)L.chunks[l] * TS_PB * TS_PB + (size_t)L.chunks[l] * TS_PB + 64;
+    // CholeskyQR2: partial Gram matrices of the level-0 chunks, R^-1, state words
+    tot += (size_t)L.chunks[0] * TS_PB * CQ_GP + TS_PB * CQ_GP + 64;
     return tot;
 }
 
 // orthonormalise one panel P (m x b, leading dimension ld) in place
 int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, const int* run_flag, cudaStream_t s) {
-    AB_ENSURE_SMEM(tsqr_apply_kernel, APPLY_SMEM);
+    static_assert(CQ_SMEM >= APPLY_SMEM, "the Householder fallback needs less dynamic shared memory than the CholeskyQR kernels");
+    AB_ENSURE_SMEM(cholqr_chunk_kernel, CQ_SMEM);
+    AB_ENSURE_SMEM(tsqr_chunk_kernel, APPLY_SMEM);
+    AB_ENSURE_SMEM(tsqr_mul_kernel, MUL_SMEM);
+    static const int force_householder = getenv("ACETN_B200_TSQR_HOUSEHOLDER") != nullptr && getenv("ACETN_B200_TSQR_HOUSEHOLDER")[0] == '1';
     Levels L = plan_levels(m, b);
     double* mat[9]; int64_t lds[9]; double* rst[8]; double* tau[8];
     mat[0] = P; lds[0] = ld;
@@ -245,13 +475,35 @@ int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, const i
         tau[l] = cur; cur += (size_t)L.chunks[l] * b + 64 - ((size_t)L.chunks[l] * b) % 2;
         mat[l + 1] = rst[l]; lds[l + 1] = b;
     }
+    double* Gpart = scratch + tsqr_scratch_doubles(m) - ((size_t)L.chunks[0] * TS_PB * CQ_GP + TS_PB * CQ_GP + 64);
+    double* Rinv = Gpart + (size_t)L.chunks[0] * TS_PB * CQ_GP;
+    int* state = reinterpret_cast<int*>(Rinv + TS_PB * CQ_GP);
+    const unsigned nch = (unsigned)L.chunks[0];
+    const int* fb_state = state;
+    if (!force_householder && m >= b) {
+        // ---- fast path: CholeskyQR2 (5 launches); every kernel after the first factorisation is a no-op once state[0] drops to 0
+        cholqr_chunk_kernel<<<nch, TS_CH, CQ_SMEM, s>>>(P, ld, m, b, Rinv, Gpart, state, run_flag, 0);
+        AB_LAUNCHED();
+        cholqr_factor_kernel<<<1, TS_CH, 0, s>>>(Gpart, (int)nch, b, Rinv, state, run_flag, 1);
+        AB_LAUNCHED();
+        cholqr_chunk_kernel<<<nch, TS_CH, CQ_SMEM, s>>>(P, ld, m, b, Rinv, Gpart, state, run_flag, 1);
+        AB_LAUNCHED();
+        cholqr_factor_kernel<<<1, TS_CH, 0, s>>>(Gpart, (int)nch, b, Rinv, state, run_flag, 2);
+        AB_LAUNCHED();
+        cholqr_chunk_kernel<<<nch, TS_CH, CQ_SMEM, s>>>(P, ld, m, b, Rinv, Gpart, state, run_flag, 2);
+        AB_LAUNCHED();
+    } else {
+        fb_state = nullptr;
+    }
+    // ---- fallback (skipped on the device when the fast path finished): Householder TSQR with explicit chunk factors.
+    // bottom-up: the R stack of level l is the matrix of level l + 1
     for (int l = 0; l < L.n; l++) {
-        tsqr_factor_kernel<<<(unsigned)L.chunks[l], TS_CH, FACTOR_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, rst[l], tau[l], run_flag);
+        tsqr_chunk_kernel<<<(unsigned)L.chunks[l], TS_CH, APPLY_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, rst[l], tau[l], fb_state, run_flag);
         AB_LAUNCHED();
     }
-    for (int l = L.n - 1; l >= 0; l--) {
-        const double* Min = (l == L.n - 1) ? nullptr : mat[l + 1];
-        tsqr_apply_kernel<<<(unsigned)L.chunks[l], TS_CH, APPLY_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, tau[l], Min, run_flag);
+    // top-down: chunk c of level l <- Q0_c * (rows of the final Q of level l + 1); the top level is final as it stands
+    for (int l = L.n - 2; l >= 0; l--) {
+        tsqr_mul_kernel<<<(unsigned)L.chunks[l], TS_CH, MUL_SMEM, s>>>(mat[l], lds[l], L.rows[l], b, mat[l + 1], fb_state, run_flag);
         AB_LAUNCHED();
     }
     return OK;
