@@ -110,3 +110,20 @@ def test_evolve_with_als_pinv_matches_reference_torch():
         ip.evolve(dtau=0.05, steps=5)
         res[b200] = float(ip.measure()["Energy"])
     assert res[True] == pytest.approx(res[False], abs=1e-8)
+
+
+def test_checkpoint_round_trip_on_b200(tmp_path):
+    """`.pt` compatibility (tensor_network.py:94-122): the reference's own save / load with backend='b200' -- the boundary tensors the
+    B200 mover produced (incl. arena tensors of the graph path) pickle, reload onto the GPU and measure to the same energy."""
+    Ipeps = setup()
+    torch.manual_seed(2)
+    ip = Ipeps(_cuda_cfg(config(CASES[0]), True))
+    ip.load(os.path.join(ref_dir(), "ipeps_gs", CASES[0] + ".pt"))
+    ip.renormalize()
+    e0 = float(ip.measure()["Energy"])
+    path = str(tmp_path / "state.pt")
+    ip.save(path)
+    ip2 = Ipeps(_cuda_cfg(config(CASES[0]), True))
+    ip2.load(path)
+    assert ip2[(0, 0)]['C'][0].is_cuda
+    assert float(ip2.measure()["Energy"]) == pytest.approx(e0, rel=1e-13)

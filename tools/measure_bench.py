@@ -18,6 +18,7 @@ def timed(f):
 res = {"D": a.D, "chi": a.chi}
 res["site_rdm_s"], _ = timed(lambda: rdm[(0, 0)])
 res["bond_rdm_s"], _ = timed(lambda: rdm[ip.bond_list[0]])
+measure(ip, orc.heisenberg_bond_hamiltonian(1.0)); torch.cuda.synchronize()      # warm-up: every kernel variant of all bond directions resident
 t = time.perf_counter(); out = measure(ip, orc.heisenberg_bond_hamiltonian(1.0)); torch.cuda.synchronize(); res["measure_s"] = time.perf_counter() - t
 res["energy"] = float(out["Energy"])
 nD = min(a.D ** 3, a.d * a.D)
