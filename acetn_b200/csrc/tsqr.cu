@@ -331,11 +331,31 @@ cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, doubl
     else if (state[0] == 0) return;
     __shared__ double G[TS_PB * CQ_GP];
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
-    for (int e = tid; e < TS_PB * TS_PB; e += TS_CH) {
-        const int i = e >> 5, k = e & 31;
-        double g = 0.0;
-        for (int ch = 0; ch < nchunks; ch++) g += Gpart[(int64_t)ch * TS_PB * CQ_GP + i * CQ_GP + k];
-        G[i * CQ_GP + k] = (i < b && k < b) ? g : (i == k ? 1.0 : 0.0);          // identity padding keeps the unrolled steps regular
+    // fixed-order sum of the partial Gram matrices; all four entries of a thread and eight chunks at a time in flight (the loads are
+    // L2 hits of ~0.5 us latency: issued one by one they would cost more than the factorisation itself)
+    {
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* base = Gpart + (tid >> 5) * CQ_GP + (tid & 31);            // entry e = tid + 256 u  ->  row (tid >> 5) + 8 u, column tid & 31
+        int ch = 0;
+        for (; ch + 8 <= nchunks; ch += 8) {
+            double v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int t = 0; t < 8; t++) v[u][t] = __ldcg(base + (int64_t)(ch + t) * TS_PB * CQ_GP + u * 8 * CQ_GP);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int t = 0; t < 8; t++) g[u] += v[u][t];
+        }
+        for (; ch < nchunks; ch++)
+#pragma unroll
+            for (int u = 0; u < 4; u++) g[u] += __ldcg(base + (int64_t)ch * TS_PB * CQ_GP + u * 8 * CQ_GP);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = (tid >> 5) + 8 * u, k = tid & 31;
+            G[i * CQ_GP + k] = (i < b && k < b) ? g[u] : (i == k ? 1.0 : 0.0);   // identity padding keeps the unrolled steps regular
+        }
     }
     __syncthreads();
     if (w != 0) return;
@@ -465,7 +485,9 @@ int tsqr_panel(double* P, int64_t m, int b, int64_t ld, double* scratch, const i
     AB_ENSURE_SMEM(cholqr_chunk_kernel, CQ_SMEM);
     AB_ENSURE_SMEM(tsqr_chunk_kernel, APPLY_SMEM);
     AB_ENSURE_SMEM(tsqr_mul_kernel, MUL_SMEM);
-    static const int force_householder = getenv("ACETN_B200_TSQR_HOUSEHOLDER") != nullptr && getenv("ACETN_B200_TSQR_HOUSEHOLDER")[0] == '1';
+    // dev / test knob, read per call: ACETN_B200_TSQR_HOUSEHOLDER=1 disables the CholeskyQR2 fast path
+    const char* fh = getenv("ACETN_B200_TSQR_HOUSEHOLDER");
+    const int force_householder = fh != nullptr && fh[0] == '1';
     Levels L = plan_levels(m, b);
     double* mat[9]; int64_t lds[9]; double* rst[8]; double* tau[8];
     mat[0] = P; lds[0] = ld;

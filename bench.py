@@ -100,6 +100,12 @@ def workload_string(args, nx, ny):
             "half-system rsvd niter=2 p=2")
 
 
+def shared_config(args, nx, ny):
+    """The `config` object is IDENTICAL in both arms (the driver compares them); arm-specific facts live under `details`."""
+    return {"workload": workload_string(args, nx, ny), "cell": f"{nx}x{ny}", "value_unit": "sweeps of 16 site-moves per second",
+            "l2": "inputs exceed the 126 MB L2 (2 GiB quarter tensors at D=8 chi=256); no flush between iterations"}
+
+
 def host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs use ALL host cores of the box."""
     import torch
@@ -247,10 +253,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_move * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_string(args, nx, ny), "cell": f"{nx}x{ny}",
-                       "value_unit": "sweeps of 16 site-moves per second",
-                       "step": "one site-move (1/16 of a value-unit sweep); ms_per_step is per site-move",
-                       "device": ("cuda (reference torch path = cuBLAS/cuSOLVER via torch)" if on_gpu else "cpu (reference torch path)")},
+            "config": shared_config(args, nx, ny),
+            "details": {"step": "one site-move (1/16 of a value-unit sweep); ms_per_step is per site-move",
+                        "device": ("cuda (reference torch path = cuBLAS/cuSOLVER via torch)" if on_gpu else "cpu (reference torch path)")},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -575,13 +580,13 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_string(args, nx, ny),
-                           "cell": f"{nx}x{ny}", "value_unit": "sweeps of 16 site-moves per second", "parallelism": f"site-sharded x{n}" + (f", {gsz} ranks per projector (row-sharded)" if n > 1 and gsz > 1 else ""),
-                           "l2": "inputs (2 GiB quarter tensors) exceed the 126 MB L2; no flush between iterations"},
+                "config": shared_config(args, nx, ny),
+                "details": {"parallelism": f"site-sharded x{n}" + (f", {gsz} ranks per projector (row-sharded)" if n > 1 and gsz > 1 else ""),
+                            },
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "peak_mem_gib": round(peak_mem_gib, 1)}
-        line["config"]["thin_engine"] = ("i8 (K7: integer products on the INT8 tensor cores, operands in 54-bit fixed point per row/column scale)"
-                                         if use_i8 else "dmma (K1)")
+        line["details"]["thin_engine"] = ("i8 (K7: integer products on the INT8 tensor cores, operands in 54-bit fixed point per row/column scale)"
+                                          if use_i8 else "dmma (K1)")
         if parity is not None:
             line["parity"] = parity
             line["parity_ok"] = parity["parity_ok"]

@@ -260,3 +260,28 @@ def test_gemm_fuzz_two_level_descriptors(seed):
     splitk = int(rng.choice([0, 0, 2, 3])) if K >= 128 else 0
     ops.gemm_ex(M, N, K, nb, A_t, B_t, C_t, a_idx + b_idx + c_idx, alpha=alpha, beta=beta, force_tile=tile, force_splitk=splitk)
     assert rel(C_d(), ref) < 1e-12
+
+
+@pytest.mark.parametrize("cond", [1e1, 1e3, 1e5, 1e7, 1e12])
+def test_orthonormalize_fast_path_matches_householder_quality(cond, monkeypatch):
+    """K4's CholeskyQR2 fast path (taken per 32-column panel when every Cholesky pivot keeps > 1e-11 of its diagonal) against the
+    Householder TSQR path on tall matrices of prescribed condition number: orthogonality at machine precision on both, and the
+    basis must capture every left singular direction u_k of Y as well as the Householder basis does (the residual of u_k outside
+    span(Q), weighted by s_k / s_0 -- what the rSVD's spectrum sees -- stays at 1e-14)."""
+    m, q = 8192, 96
+    g = torch.Generator().manual_seed(17)
+    U = torch.linalg.qr(torch.randn(m, q, dtype=torch.float64, generator=g)).Q.cuda()
+    V = torch.linalg.qr(torch.randn(q, q, dtype=torch.float64, generator=g)).Q.cuda()
+    s = torch.logspace(0, -torch.log10(torch.tensor(cond)).item(), q, dtype=torch.float64, device="cuda")
+    Y = (U * s) @ V.T
+    res = {}
+    for name, flag in (("fast", "0"), ("householder", "1")):
+        monkeypatch.setenv("ACETN_B200_TSQR_HOUSEHOLDER", flag)
+        Q = ops.orthonormalize(Y.clone())
+        orth = float((Q.T @ Q - torch.eye(q, dtype=torch.float64, device="cuda")).abs().max())
+        resid = (U - Q @ (Q.T @ U)).norm(dim=0) * s / s[0]            # weighted residual per singular direction
+        res[name] = (orth, float(resid.max()))
+    print(f"cond {cond:.0e}: fast (orth, weighted residual) = {res['fast']}, householder = {res['householder']}")
+    for name in res:
+        assert res[name][0] < 5e-14, (name, res[name])
+        assert res[name][1] < 1e-13, (name, res[name])
