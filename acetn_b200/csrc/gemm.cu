@@ -28,6 +28,7 @@ struct GemmKernelParams {
     double* ws;          // split-K partials [batch*splitk][M][N] (dense) when splitk > 1
     int a_vec, b_vec;    // 16-byte loads allowed along the contiguous index
     int fast;            // both k indices single-level and both operands vectorisable: pointer-increment loader
+    int c_vec;           // adjacent output columns are adjacent in memory and 16-byte aligned: paired stores
 };
 
 template <int BM, int BN, bool A_MC, bool B_KC, int BK>
@@ -43,6 +44,74 @@ struct SmemLayout {
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
     static constexpr size_t BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
 };
+
+// Epilogue store of one warp's accumulators: C = alpha * acc + beta * C through the two-level output descriptors.
+// DMUL / DSETP run on the same FP64 datapath as the DMMAs of the co-resident warps and queue behind them (the epilogue was
+// 15-20 % of a warp's life in the K = chi class, profiles/r02_ncu_k1_epilogue.txt), so the common alpha = 1, beta = 0 case
+// issues no FP64 instruction at all, and adjacent column pairs go out as one 16-byte store when the n index is contiguous.
+template <int MT, int NTL>
+__device__ __forceinline__ void store_accumulators(const GemmKernelParams& p, double (&acc)[MT][NTL][2], int b, int mw, int nw,
+                                                   int lr, int lc) {
+    double* Cb = p.C + p.cb.off(b);
+    const bool has_beta = p.beta != 0.0;
+    const bool scale = p.alpha != 1.0;
+    if (p.c_vec) {
+        int64_t noff[NTL];
+        bool pair[NTL];
+#pragma unroll
+        for (int j = 0; j < NTL; j++) {
+            int n = nw + j * 8 + 2 * lc;
+            noff[j] = n < p.N ? p.cn.off(n) : -1;
+            pair[j] = n + 1 < p.N;
+        }
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+            int m = mw + i * 8 + lr;
+            if (m >= p.M) continue;
+            double* row = Cb + p.cm.off(m);
+#pragma unroll
+            for (int j = 0; j < NTL; j++) {
+                if (noff[j] < 0) continue;
+                double* dst = row + noff[j];
+                double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                if (scale) { v0 *= p.alpha; v1 *= p.alpha; }
+                if (pair[j]) {
+                    if (has_beta) { double2 o = *reinterpret_cast<const double2*>(dst); v0 += p.beta * o.x; v1 += p.beta * o.y; }
+                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                } else {
+                    if (has_beta) v0 += p.beta * (*dst);
+                    *dst = v0;
+                }
+            }
+        }
+        return;
+    }
+    int64_t noff[NTL][2];
+#pragma unroll
+    for (int j = 0; j < NTL; j++) {
+        int n = nw + j * 8 + 2 * lc;
+        noff[j][0] = n < p.N ? p.cn.off(n) : -1;
+        noff[j][1] = n + 1 < p.N ? p.cn.off(n + 1) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+        int m = mw + i * 8 + lr;
+        if (m >= p.M) continue;
+        double* row = Cb + p.cm.off(m);
+#pragma unroll
+        for (int j = 0; j < NTL; j++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (noff[j][e] < 0) continue;
+                double* dst = row + noff[j][e];
+                double v = acc[i][j][e];
+                if (scale) v *= p.alpha;
+                if (has_beta) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
 
 template <int BM, int BN, int WM, int WN, bool A_MC, bool B_KC, int BK>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
@@ -317,31 +386,7 @@ dgemm_dmma_kernel(const GemmKernelParams p) {
         }
         return;
     }
-    double* Cb = p.C + p.cb.off(b);
-    int64_t noff[NTL][2];
-#pragma unroll
-    for (int j = 0; j < NTL; j++) {
-        int n = n0 + wn0 + j * 8 + 2 * lc;
-        noff[j][0] = n < p.N ? p.cn.off(n) : -1;
-        noff[j][1] = n + 1 < p.N ? p.cn.off(n + 1) : -1;
-    }
-#pragma unroll
-    for (int i = 0; i < MT; i++) {
-        int m = m0 + wm0 + i * 8 + lr;
-        if (m >= p.M) continue;
-        int64_t mo = p.cm.off(m);
-#pragma unroll
-        for (int j = 0; j < NTL; j++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                if (noff[j][e] < 0) continue;
-                double* dst = Cb + mo + noff[j][e];
-                double v = p.alpha * acc[i][j][e];
-                if (p.beta != 0.0) v += p.beta * (*dst);
-                *dst = v;
-            }
-        }
-    }
+    store_accumulators<MT, NTL>(p, acc, b, m0 + wm0, n0 + wn0, lr, lc);
 }
 
 // split-K reduction + general store:  C = alpha * sum_z ws[b][z] + beta * C
@@ -446,6 +491,12 @@ int launch_cfg(const GemmKernelParams& kp, cudaStream_t stream) {
     return OK;
 }
 
+// pointer-increment loader: both operands vectorisable and every k index either single level or two-level with div | BK
+bool fast_loader_ok(const GemmDesc& d, const Plan& pl) {
+    auto k_fast = [&](const Idx2& x) { return x.div == 0 || (x.div > 0 && x.div <= (uint32_t)pl.bk && pl.bk % x.div == 0); };
+    return pl.a_vec && pl.b_vec && k_fast(d.A.col) && k_fast(d.B.row);
+}
+
 template <int BM, int BN, int WM, int WN, int BK = BK_DEFAULT>
 int launch_orient(const GemmKernelParams& kp, bool a_mc, bool b_kc, cudaStream_t stream) {
     if (!a_mc && !b_kc) return launch_cfg<BM, BN, WM, WN, false, false, BK>(kp, stream);
@@ -475,9 +526,8 @@ int gemm_launch(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t strea
     kp.A = d.A; kp.B = d.B; kp.C = d.C; kp.cm = d.cm; kp.cn = d.cn; kp.cb = d.cb;
     kp.alpha = d.alpha; kp.beta = d.beta;
     kp.a_vec = pl.a_vec; kp.b_vec = pl.b_vec;
-    // pointer-increment loader: both operands vectorisable and every k index either single level or two-level with div | BK
-    auto k_fast = [&](const Idx2& x) { return x.div == 0 || (x.div > 0 && x.div <= pl.bk && pl.bk % x.div == 0); };
-    kp.fast = (pl.a_vec && pl.b_vec && k_fast(d.A.col) && k_fast(d.B.row)) ? 1 : 0;
+    kp.fast = fast_loader_ok(d, pl) ? 1 : 0;
+    kp.c_vec = ((((uintptr_t)d.C) & 15) == 0 && contig_ok(d.cn) && strides_even(d.cm) && strides_even(d.cb)) ? 1 : 0;
     kp.ws = nullptr;
     if (pl.splitk > 1) {
         size_t need = (size_t)d.M * d.N * d.batch * pl.splitk * sizeof(double);

@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--D", type=int, default=8)
     ap.add_argument("--chi", type=int, default=256)
-    ap.add_argument("--d", type=int, default=2)
+    ap.add_argument("--d", "--phys", dest="d", type=int, default=2, help="physical dimension (use --phys under torchrun: its parser claims --d)")
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)

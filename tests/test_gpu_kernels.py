@@ -77,6 +77,41 @@ def test_gemm_two_level_and_batched(D):
     assert rel(Cb, A @ B) < 1e-13
 
 
+def test_gemm_epilogue_paired_and_scalar_stores():
+    """K1's epilogue writes adjacent column pairs as one 16-byte store when the n index of C is contiguous and aligned
+    (gemm.cu store_accumulators) and falls back to scalar stores otherwise; alpha = 1 / beta = 0 skips the FP64 scaling.
+    Ragged edges, odd leading dimension (scalar path), batches with beta != 0, the two-level contraction class."""
+    A, B = rnd(2763, 48, seed=21), rnd(48, 2901, seed=22)       # N odd: rows of C start at odd offsets -> scalar stores
+    assert rel(ops.matmul(A, B, force_tile=3), A @ B) < 1e-13
+    At, Bn = rnd(64, 2890, seed=23), rnd(64, 2800, seed=24)     # paired stores, ragged M
+    assert rel(ops.matmul(At, Bn, transpose_a=True, force_tile=3), At.T @ Bn) < 1e-13
+    for tile in (1, 2, 3):
+        A2, B2 = rnd(333, 40, seed=30 + tile), rnd(40, 301, seed=40 + tile)   # last column unpaired
+        assert rel(ops.matmul(A2, B2, force_tile=tile), A2 @ B2) < 1e-13
+    nb, M, N, K = 3, 1600, 1700, 32
+    Ab, Bb, C0 = rnd(nb, M, K, seed=25), rnd(nb, K, N, seed=26), rnd(nb, M, N, seed=27)
+    idx = [0, 0, K, 0, 0, 1, 0, 0, M * K] + [0, 0, N, 0, 0, 1, 0, 0, K * N] + [0, 0, N, 0, 0, 1, 0, 0, M * N]
+    Cb = C0.clone()
+    ops.gemm_ex(M, N, K, nb, Ab, Bb, Cb, idx, alpha=0.5, beta=-1.5, force_tile=3)
+    assert rel(Cb, 0.5 * Ab @ Bb - 1.5 * C0) < 1e-13
+    # the 2 chi^3 D^4 contraction class of projectors.py:53 (two-level n index on B), D = 4
+    D, xa, xc, xe = 4, 64, 170, 172
+    D2 = D * D
+    T1, E1 = rnd(xa, xc * D2, seed=28), rnd(xe, xa, D, D, seed=29)
+    idx = [0, 0, 1, 0, 0, xc * D2, 0, 0, 0] + [0, 0, D2, D2, xa * D2, 1, 0, 0, 0] + [0, 0, xe * D2, 0, 0, 1, 0, 0, 0]
+    Cc = torch.empty(xc * D2, xe * D2, dtype=torch.float64, device=DEV)
+    ops.gemm_ex(xc * D2, xe * D2, xa, 1, T1, E1, Cc, idx, force_tile=3)
+    ref = torch.einsum("am,eal->mel", T1, E1.reshape(xe, xa, D2)).reshape(xc * D2, xe * D2)
+    assert rel(Cc, ref) < 1e-13
+    # C written through a transposed descriptor (n index strided): scalar path
+    M, N, K = 130, 70, 48
+    A3, B3 = rnd(M, K, seed=50), rnd(K, N, seed=51)
+    Ct = torch.empty(N, M, dtype=torch.float64, device=DEV)
+    idx = [0, 0, K, 0, 0, 1, 0, 0, 0] + [0, 0, N, 0, 0, 1, 0, 0, 0] + [0, 0, 1, 0, 0, M, 0, 0, 0]
+    ops.gemm_ex(M, N, K, 1, A3, B3, Ct, idx)
+    assert rel(Ct, (A3 @ B3).T) < 1e-13
+
+
 # ---------------------------------------------------------------------------------------------- K4 TSQR
 @pytest.mark.parametrize("m,q", [(300, 20), (1000, 64), (4097, 130), (16384, 258), (80, 22), (40, 40), (257, 33)])
 def test_orthonormalize_random(m, q):
