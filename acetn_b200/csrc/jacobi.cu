@@ -7,6 +7,7 @@
 // stays L2 resident and the steps are separated by a cooperative grid barrier.  Rotations use the relative
 // criterion |x_p.x_q| <= tol ||x_p|| ||x_q||, which gives high relative accuracy of small singular values.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -147,6 +148,134 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
     if (blockIdx.x == 0 && threadIdx.x == 0) p.info[0] = sweep;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Small cores (q <= JS_MAX_Q: X and J fit the shared memory of one SM): the whole SVD -- initialisation from R, the cyclic
+// one-sided Jacobi sweeps, singular values, sort, truncation count and the emission of W^T and J^T -- in ONE kernel on ONE
+// CTA.  No grid barrier and no L2 round trip per phase: a rotation step costs one __syncthreads.  A row pair is owned by a
+// group of JS_GROUP lanes, so the n/2 <= 56 independent pairs of a step all run at once on the CTA's 64 groups.
+// At q = 66 (D = 4, chi = 64) the multi-CTA kernel above took 0.73 ms = 27 % of a sweep (profiles/r02_small_configs.txt).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int JS_THREADS = 512;
+constexpr int JS_GROUP = 8;      // lanes per row pair.  FP64 warp instructions cost the same pipe time however many lanes are active, and the
+                                 // scalar rotation chain (sqrt, division, rsqrt: ~60 of them) is per pair: four pairs per warp instead of two
+                                 // halve the instruction stream of a step; with 16 lanes per pair the step was bound by the SM's FP64 issue rate
+constexpr int JS_MAX_Q = 112;
+
+struct JacobiSmallParams {
+    const double* R;     // q x q, row major
+    int q, n, ld;        // n = q rounded up to even rows (a zero row never rotates), ld = even row pitch
+    int max_sweeps, chi;
+    double tol, cutoff;
+    double* S;           // [q] descending
+    double* Wt;          // [q][q]
+    double* Jt;          // [q][q]
+    int* count;          // [0] kept rank, [1] sweeps used
+};
+
+__device__ __forceinline__ int rotate_pair_group(double* xa, double* xb, double* ja, double* jb, int ncols2, double tol, int gl) {
+    // the groups of a warp own different pairs (or none): shuffles name only the lanes of this group
+    const unsigned gmask = ((1u << JS_GROUP) - 1u) << (threadIdx.x & (32 - JS_GROUP));
+    double2* xa2 = reinterpret_cast<double2*>(xa);
+    double2* xb2 = reinterpret_cast<double2*>(xb);
+    double saa = 0.0, sbb = 0.0, sab = 0.0;
+    for (int c = gl; c < ncols2; c += JS_GROUP) {
+        double2 u = xa2[c], v = xb2[c];
+        saa += u.x * u.x + u.y * u.y; sbb += v.x * v.x + v.y * v.y; sab += u.x * v.x + u.y * v.y;
+    }
+#pragma unroll
+    for (int o = JS_GROUP / 2; o > 0; o >>= 1) {
+        saa += __shfl_xor_sync(gmask, saa, o);
+        sbb += __shfl_xor_sync(gmask, sbb, o);
+        sab += __shfl_xor_sync(gmask, sab, o);
+    }
+    if (saa == 0.0 || sbb == 0.0) return 0;
+    const double r2 = sab * sab, den = saa * sbb;
+    if (r2 <= tol * tol * den) return 0;
+    const double d = sbb - saa;
+    const double h = sqrt(d * d + 4.0 * r2);
+    double t = (2.0 * sab) / (fabs(d) + h);
+    t = d >= 0.0 ? t : -t;
+    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+    double2* ja2 = reinterpret_cast<double2*>(ja);
+    double2* jb2 = reinterpret_cast<double2*>(jb);
+    for (int c = gl; c < ncols2; c += JS_GROUP) {
+        double2 u = xa2[c], v = xb2[c], r;
+        r.x = cs * u.x - sn * v.x; r.y = cs * u.y - sn * v.y; xa2[c] = r;
+        r.x = sn * u.x + cs * v.x; r.y = sn * u.y + cs * v.y; xb2[c] = r;
+        double2 ju = ja2[c], jv = jb2[c];
+        r.x = cs * ju.x - sn * jv.x; r.y = cs * ju.y - sn * jv.y; ja2[c] = r;
+        r.x = sn * ju.x + cs * jv.x; r.y = sn * ju.y + cs * jv.y; jb2[c] = r;
+    }
+    return 1;
+}
+
+__global__ void __launch_bounds__(JS_THREADS, 1) jacobi_small_kernel(const JacobiSmallParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = p.n, ld = p.ld, q = p.q;
+    double* Xs = sm;                         // [n][ld]
+    double* Js = Xs + (size_t)n * ld;        // [n][ld]
+    double* sig = Js + (size_t)n * ld;       // [n]
+    double* Ssorted = sig + n;               // [n]
+    int* rank = reinterpret_cast<int*>(Ssorted + n);   // [n]
+    const int tid = threadIdx.x, grp = tid / JS_GROUP, gl = tid % JS_GROUP;
+    for (int idx = tid; idx < n * ld; idx += JS_THREADS) {
+        const int r = idx / ld, c = idx - r * ld;
+        Xs[idx] = (r < q && c < q) ? p.R[(size_t)r * q + c] : 0.0;
+        Js[idx] = (r == c && r < q) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int npairs = n / 2, nm1 = n - 1, ncols2 = ld / 2;
+    int sweep = 0;
+    for (; sweep < p.max_sweeps; sweep++) {
+        int rotated = 0;
+        for (int t = 0; t < nm1; t++) {
+            if (grp < npairs) {
+                int a, b;
+                if (grp == 0) { a = nm1; b = t; }
+                else { a = (t + grp) % nm1; b = (t - grp + nm1) % nm1; }
+                rotated |= rotate_pair_group(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, gl);
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(rotated)) { sweep++; break; }    // a sweep without any rotation: converged
+    }
+    // singular values = row norms; sort descending (rank by counting, stable); emit normalised rows
+    for (int r = grp; r < n; r += JS_THREADS / JS_GROUP) {
+        double s2 = 0.0;
+        for (int c = gl; c < q; c += JS_GROUP) { const double v = Xs[(size_t)r * ld + c]; s2 += v * v; }
+#pragma unroll
+        for (int o = JS_GROUP / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(((1u << JS_GROUP) - 1u) << (threadIdx.x & (32 - JS_GROUP)), s2, o);
+        if (gl == 0) sig[r] = sqrt(s2);
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += JS_THREADS) {
+        const double sr = sig[r];
+        int k = 0;
+        for (int o = 0; o < n; o++) { const double so = sig[o]; k += (so > sr) || (so == sr && o < r); }
+        rank[r] = k;
+        Ssorted[k] = sr;
+        if (k < q) p.S[k] = sr;
+    }
+    __syncthreads();
+    for (int r = grp; r < n; r += JS_THREADS / JS_GROUP) {
+        const int k = rank[r];
+        if (k >= q) continue;
+        const double sr = sig[r];
+        const double inv = sr > 0.0 ? 1.0 / sr : 0.0;
+        for (int c = gl; c < q; c += JS_GROUP) {
+            p.Wt[(size_t)k * q + c] = Xs[(size_t)r * ld + c] * inv;
+            p.Jt[(size_t)k * q + c] = Js[(size_t)r * ld + c];
+        }
+    }
+    if (tid == 0) {
+        const double s0 = Ssorted[0];
+        int k = 0;
+        for (int i = 0; i < q; i++) k += (Ssorted[i] / s0 > p.cutoff) ? 1 : 0;
+        p.count[0] = k < p.chi ? k : p.chi;
+        p.count[1] = sweep;
+    }
+}
+
 __global__ void jacobi_init_kernel(double* X, double* J, const double* R, int q, int n, int ld) {
     size_t total = (size_t)n * ld;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -227,8 +356,22 @@ size_t jacobi_workspace_bytes(int q) {
 int jacobi_svd_launch(const double* R, int q, double* S, double* Wt, double* Jt, int chi, double cutoff, int* count,
                       void* wsp, size_t ws_bytes, cudaStream_t s) {
     AB_REQUIRE(q >= 1 && q <= 3400, "jacobi_svd: q=%d out of range (1..3400)", q);
-    const JacobiGeom g = jacobi_geom(q);
     const int max_sweeps = 60;
+    {
+        // small cores: everything in one kernel on one CTA (ACETN_B200_JACOBI_SMALL=0 keeps the multi-CTA kernel: dev / test knob)
+        const char* e = getenv("ACETN_B200_JACOBI_SMALL");
+        if (q <= JS_MAX_Q && !(e != nullptr && e[0] == '0')) {
+            JacobiSmallParams sp;
+            sp.R = R; sp.q = q; sp.n = q + (q & 1); sp.ld = q + (q & 1); sp.max_sweeps = max_sweeps; sp.chi = chi;
+            sp.tol = 2.3e-16 * sqrt((double)(q > 64 ? q : 64)); sp.cutoff = cutoff; sp.S = S; sp.Wt = Wt; sp.Jt = Jt; sp.count = count;
+            const size_t smem = ((size_t)2 * sp.n * sp.ld + 2 * sp.n) * sizeof(double) + (size_t)sp.n * sizeof(int) + 16;
+            AB_ENSURE_SMEM(jacobi_small_kernel, smem);
+            jacobi_small_kernel<<<1, JS_THREADS, smem, s>>>(sp);
+            AB_LAUNCHED();
+            return OK;
+        }
+    }
+    const JacobiGeom g = jacobi_geom(q);
     Workspace ws(wsp, ws_bytes);
     double* X = ws.take<double>((size_t)g.n * g.ld);
     double* J = ws.take<double>((size_t)g.n * g.ld);

@@ -15,6 +15,7 @@
 //     cond 1e20 (SURVEY.md section 7 hard part 2), where CholeskyQR would lose the trailing directions; such panels fail the pivot
 //     test and take this path, while well-conditioned panels (the first and last orthonormalisation of a projector, random benchmark
 //     tensors) take the short one.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -45,7 +46,7 @@ struct FactorSmem {
 };
 
 __device__ __forceinline__ void tsqr_factor_body(double* __restrict__ P, int64_t ld, int64_t nrows, int b, double* __restrict__ Rstack,
-                                                 double* __restrict__ tau_out, FactorSmem& fs) {
+                                                 double* __restrict__ tau_out, FactorSmem& fs, int chunk) {
     double (&col_s)[TS_CH] = fs.col_s;
     double (&part)[TS_NW][TS_PB] = fs.part;
     double (&partn)[TS_NW] = fs.partn;
@@ -53,7 +54,7 @@ __device__ __forceinline__ void tsqr_factor_body(double* __restrict__ P, int64_t
     double (&beta_s)[TS_PB] = fs.beta_s;
     double (&scale_s)[TS_PB] = fs.scale_s;
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
-    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int64_t r0 = (int64_t)chunk * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
     const int nref = b < rows ? b : rows;
     const int rbase = 32 * w;
@@ -149,21 +150,21 @@ __device__ __forceinline__ void tsqr_factor_body(double* __restrict__ P, int64_t
             double v = x[i];
             if (has_ref) v = r > c ? v * sc : (r == c ? be : v);
             if (r < rows && c < b) P[(r0 + r) * ld + c] = v;
-            if (r < b && c < b) Rstack[((int64_t)blockIdx.x * b + r) * b + c] = (r <= c && r < nref) ? v : 0.0;
+            if (r < b && c < b) Rstack[((int64_t)chunk * b + r) * b + c] = (r <= c && r < nref) ? v : 0.0;
         }
     }
-    if (tid < b) tau_out[(int64_t)blockIdx.x * b + tid] = tau_s[tid];
+    if (tid < b) tau_out[(int64_t)chunk * b + tid] = tau_s[tid];
 }
 
 // Form the explicit Q rows of one chunk: Q_chunk = H_0 ... H_{b-1} [M; 0], M = Min rows [chunk*b, chunk*b + b) (identity if null).
 __device__ __forceinline__ void tsqr_apply_body(double* __restrict__ P, int64_t ld, int64_t nrows, int b, const double* __restrict__ tau_in,
-                                                const double* __restrict__ Min, double* sm) {
+                                                const double* __restrict__ Min, double* sm, int chunk) {
     constexpr int VP = TS_CH + 2;                  // even pitch: 16-byte aligned rows for LDS.128 reads of the reflectors
     double* Vs = sm;                               // [TS_PB][VP]: reflector j with unit diagonal, zeros above
     double* part = sm + TS_PB * VP;             // [2][TS_NW][TS_PB]
     double* tau_s = part + 2 * TS_NW * TS_PB;      // [TS_PB]
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
-    const int64_t r0 = (int64_t)blockIdx.x * TS_CH;
+    const int64_t r0 = (int64_t)chunk * TS_CH;
     const int rows = (int)((nrows - r0) < TS_CH ? (nrows - r0) : TS_CH);
     const int nref = b < rows ? b : rows;
     const int rbase = 32 * w;
@@ -175,10 +176,10 @@ __device__ __forceinline__ void tsqr_apply_body(double* __restrict__ P, int64_t 
         double v = (r < rows && c < b) ? P[(r0 + r) * ld + c] : 0.0;
         Vs[c * VP + r] = (r > c) ? v : (r == c ? 1.0 : 0.0);
         double zz = 0.0;
-        if (r < nref && c < b) zz = Min ? Min[((int64_t)blockIdx.x * b + r) * b + c] : (r == c ? 1.0 : 0.0);
+        if (r < nref && c < b) zz = Min ? Min[((int64_t)chunk * b + r) * b + c] : (r == c ? 1.0 : 0.0);
         z[i] = zz;
     }
-    if (tid < TS_PB) tau_s[tid] = tid < b ? tau_in[(int64_t)blockIdx.x * b + tid] : 0.0;
+    if (tid < TS_PB) tau_s[tid] = tid < b ? tau_in[(int64_t)chunk * b + tid] : 0.0;
     __syncthreads();
 
     int buf = 0;
@@ -254,10 +255,26 @@ __device__ __forceinline__ void chunk_times_matrix(double (&x)[32], const double
 #pragma unroll
     for (int i = 0; i < 32; i++) x[i] = acc[i];
 }
+// x[i] (rows 32w+i of column c)  -=  sum_{k < 32} X[row][k] * M[k][c]   (block classical Gram-Schmidt update inside the fused kernel)
+__device__ __forceinline__ void chunk_minus_times_matrix(double (&x)[32], const double* __restrict__ Xt, const double* __restrict__ M, int mp, int w,
+                                                         int c) {
+    for (int k = 0; k < TS_PB; k++) {
+        const double m = -M[k * mp + c];
+        const double2* src = reinterpret_cast<const double2*>(Xt + k * CQ_XP + 32 * w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const double2 t = src[i];
+            x[2 * i] = fma(t.x, m, x[2 * i]);
+            x[2 * i + 1] = fma(t.y, m, x[2 * i + 1]);
+        }
+    }
+}
 // partial Gram matrix of this CTA's chunk -> Gout[32][CQ_GP] (global): G[c][k] = sum_rows X[r][c] X[r][k]
 // (every thread accumulates its column against all b columns over its warp's 32 rows; 8-way reduction through shared memory)
+// (bi = number of valid columns on the x side; the fused kernel multiplies a full 32-column block of Q by a narrower panel)
 __device__ __forceinline__ void chunk_gram(const double (&x)[32], const double* __restrict__ Xt, double* __restrict__ part, int b, int w, int c,
-                                           double* __restrict__ Gout) {
+                                           double* __restrict__ Gout, int bi = -1) {
+    if (bi < 0) bi = b;
     for (int k = 0; k < b; k += 2) {
         const double2* s0 = reinterpret_cast<const double2*>(Xt + k * CQ_XP + 32 * w);
         const double2* s1 = reinterpret_cast<const double2*>(Xt + (k + 1) * CQ_XP + 32 * w);      // k + 1 <= 31: inside Xt (zero column if >= b)
@@ -281,7 +298,7 @@ __device__ __forceinline__ void chunk_gram(const double (&x)[32], const double* 
         double g = 0.0;
 #pragma unroll
         for (int ww = 0; ww < TS_NW; ww++) g += part[(ww * TS_PB + i) * CQ_GP + k];
-        Gout[i * CQ_GP + k] = (i < b && k < b) ? g : 0.0;
+        Gout[i * CQ_GP + k] = (i < bi && k < b) ? g : 0.0;
     }
 }
 constexpr size_t CQ_SMEM = (size_t)(TS_PB * CQ_XP + TS_NW * TS_PB * CQ_GP + TS_PB * CQ_GP) * sizeof(double);
@@ -323,13 +340,10 @@ cholqr_chunk_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, co
 // fully unrolled steps of shuffles + FMAs), R^-1 by back substitution.  pass 1: the factorisation is accepted only if every pivot
 // keeps more than CQ_PIVOT_TOL of its diagonal entry, otherwise state[0] <- 0 (Householder path).  pass 2: G is I + O(eps cond^2);
 // a failed pivot there also hands the (already better conditioned) panel to the Householder path; success sets state[1].
-__global__ void __launch_bounds__(TS_CH, 1)
-cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, double* __restrict__ Rinv, int* __restrict__ state,
-                     const int* __restrict__ run_flag, int pass) {
-    if (run_flag != nullptr && *run_flag == 0) return;
-    if (pass == 1) { if (threadIdx.x == 0) { state[0] = 1; state[1] = 0; } }
-    else if (state[0] == 0) return;
-    __shared__ double G[TS_PB * CQ_GP];
+// Body shared by cholqr_factor_kernel and the fused kernel.  All 256 threads take part in the reduction; warp 0 factors.  Returns (in
+// every thread of warp 0; other warps get `true`) whether every pivot passed the test.  G: shared scratch [32][CQ_GP]; Rinv: [32][CQ_GP],
+// global or shared.  Ends with the warp-0 writes outstanding: the caller synchronises before anybody reads Rinv.
+__device__ __forceinline__ bool cholqr_factor_body(const double* __restrict__ Gpart, int nchunks, int b, double* __restrict__ Rinv, double* __restrict__ G) {
     const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
     // fixed-order sum of the partial Gram matrices; all four entries of a thread and eight chunks at a time in flight (the loads are
     // L2 hits of ~0.5 us latency: issued one by one they would cost more than the factorisation itself)
@@ -358,7 +372,7 @@ cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, doubl
         }
     }
     __syncthreads();
-    if (w != 0) return;
+    if (w != 0) return true;
     double g[TS_PB], dinv[TS_PB];
 #pragma unroll
     for (int i = 0; i < TS_PB; i++) g[i] = G[i * CQ_GP + c];
@@ -392,7 +406,18 @@ cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, doubl
     }
 #pragma unroll
     for (int i = 0; i < TS_PB; i++) Rinv[i * CQ_GP + c] = sv[i];
-    if (c == 0) {
+    return good;
+}
+
+__global__ void __launch_bounds__(TS_CH, 1)
+cholqr_factor_kernel(const double* __restrict__ Gpart, int nchunks, int b, double* __restrict__ Rinv, int* __restrict__ state,
+                     const int* __restrict__ run_flag, int pass) {
+    if (run_flag != nullptr && *run_flag == 0) return;
+    if (pass == 1) { if (threadIdx.x == 0) { state[0] = 1; state[1] = 0; } }
+    else if (state[0] == 0) return;
+    __shared__ double G[TS_PB * CQ_GP];
+    const bool good = cholqr_factor_body(Gpart, nchunks, b, Rinv, G);
+    if (threadIdx.x == 0) {
         if (!good) state[0] = 0;
         else if (pass == 2) state[1] = 1;
     }
@@ -409,9 +434,9 @@ tsqr_chunk_kernel(double* __restrict__ P, int64_t ld, int64_t nrows, int b, doub
     if (state != nullptr && state[1] != 0) return;        // CholeskyQR2 finished the panel
     extern __shared__ __align__(16) double sm[];
     __shared__ FactorSmem fs;
-    tsqr_factor_body(P, ld, nrows, b, Rstack, tau_scratch, fs);
+    tsqr_factor_body(P, ld, nrows, b, Rstack, tau_scratch, fs, blockIdx.x);
     __syncthreads();
-    tsqr_apply_body(P, ld, nrows, b, tau_scratch, nullptr, sm);
+    tsqr_apply_body(P, ld, nrows, b, tau_scratch, nullptr, sm, blockIdx.x);
 }
 
 // Q chunk c of a level  <-  Q0_c * M_c,  M_c = rows [c b, c b + b) of the final explicit Q of the next level (ld = b)
@@ -449,6 +474,171 @@ __global__ void bcgs_flag_kernel(const double* __restrict__ c, int n, double thr
     if (mine) any = 1;
     __syncthreads();
     if (threadIdx.x == 0) *run_flag = any;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused orthonormalisation for small tall matrices (m <= FUSED_MAX_ROWS, q <= FUSED_MAX_COLS): the WHOLE algorithm above --
+// every panel, both BCGS passes, CholeskyQR2 with its pivot test and the Householder TSQR fallback -- in ONE cooperative
+// kernel, one CTA per 256-row chunk, grid barriers where the multi-launch path has kernel boundaries.  At these sizes the
+// multi-launch path is ~25 dependent launches of 1-8 us per panel (launch-latency bound: 58 % of the launches and half of the
+// kernel time of a D=4, chi=64 sweep); the matrix (<= 4 MB) stays in L2 between the stages.  Same arithmetic in the same
+// order per chunk as the multi-launch path except for the inter-panel projections, which use the chunk kernels' FMA code
+// instead of K1 (results agree to rounding, not bit for bit).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FUSED_MAX_ROWS = 4096;     // <= 16 CTAs: a cooperative grid this small is always co-resident next to the bulk kernels
+constexpr int FUSED_MAX_COLS = 130;      // coefficient block of the projections lives in shared memory
+
+struct OrthoFusedParams {
+    double* Y;
+    int64_t ld;
+    int m, q, nchunks, force_householder;
+    double* Spart;       // [nchunks][q/32 blocks][32][CQ_GP]  partial projection coefficients
+    double* Gpart[2];    // [nchunks][32][CQ_GP]  partial Gram matrices of the two CholeskyQR passes
+    // Householder levels (as in tsqr_panel): the R stack rst[l] of level l is the matrix of level l + 1 (sized for 32-column panels)
+    double* rst[4];
+    double* tau[4];
+};
+
+// SYNC: how the CTAs (one per chunk) meet between stages.  0: a single CTA, __syncthreads.  1: one thread-block cluster (<= 8 CTAs),
+// hardware cluster barrier with release/acquire -- an ordinary launch, which also replays inside CUDA graphs next to other branches.
+// 2: cooperative grid barrier (9..16 CTAs).
+template <int SYNC>
+__device__ __forceinline__ void fused_sync() {
+    if (SYNC == 0) __syncthreads();
+    else if (SYNC == 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else cooperative_groups::this_grid().sync();
+}
+
+template <int SYNC>
+__global__ void __launch_bounds__(TS_CH, 1) ortho_fused_kernel(const OrthoFusedParams p) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ FactorSmem fs;
+    __shared__ int s_flag;
+    double* Xt = sm;                                   // [32][CQ_XP]   staged panel / block, transposed
+    double* part = Xt + TS_PB * CQ_XP;                 // [8 * 32][CQ_GP]
+    double* Ms = part + TS_NW * TS_PB * CQ_GP;         // [32][CQ_GP]   R^-1 / M block
+    double* Gs = Ms + TS_PB * CQ_GP;                   // [32][CQ_GP]   Gram scratch
+    double* Ss = Gs + TS_PB * CQ_GP;                   // [q32][CQ_GP]  projection coefficients
+    const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
+    const int chunk = blockIdx.x;
+    const int64_t r0 = (int64_t)chunk * TS_CH;
+    const int rows = (int)((p.m - r0) < TS_CH ? (p.m - r0) : TS_CH);
+    const int nblk_max = (p.q + TS_PB - 1) / TS_PB;
+    double xp[32], xq[32];
+
+    for (int j0 = 0; j0 < p.q; j0 += TS_PB) {
+        const int b = (p.q - j0) < TS_PB ? (p.q - j0) : TS_PB;
+        double* P = p.Y + j0;
+        const int nblk = j0 / TS_PB;
+        for (int pass = 0; pass < 2; pass++) {
+            if (j0 == 0 && pass == 1) break;
+            chunk_load(xp, P, p.ld, r0, rows, b, w, c);
+            if (j0 > 0) {
+                // ---- coefficients of the panel against the finished columns: S = Q_prev^T P, chunk partials then a fixed-order sum
+                __syncthreads();
+                chunk_stage(xp, Xt, w, c);
+                __syncthreads();
+                for (int ib = 0; ib < nblk; ib++) {
+                    chunk_load(xq, p.Y + ib * TS_PB, p.ld, r0, rows, TS_PB, w, c);
+                    chunk_gram(xq, Xt, part, b, w, c, p.Spart + ((int64_t)(chunk * nblk_max + ib) * TS_PB) * CQ_GP, TS_PB);
+                    __syncthreads();
+                }
+                fused_sync<SYNC>();
+                double mx = 0.0;
+                for (int e = tid; e < nblk * TS_PB * TS_PB; e += TS_CH) {
+                    const int ib = e / (TS_PB * TS_PB), r = e - ib * TS_PB * TS_PB, i = r >> 5, k = r & 31;
+                    double sacc = 0.0;
+                    for (int ch = 0; ch < p.nchunks; ch++) sacc += __ldcg(p.Spart + ((int64_t)(ch * nblk_max + ib) * TS_PB + i) * CQ_GP + k);
+                    Ss[(ib * TS_PB + i) * CQ_GP + k] = sacc;
+                    mx = fmax(mx, fabs(sacc));
+                }
+                if (tid == 0) s_flag = 0;
+                __syncthreads();
+                // "twice is enough": with second-pass coefficients below 1e-10 the update below leaves the panel orthonormal to O(1e-20),
+                // so its re-factorisation is skipped (uniform decision: every CTA sums the same numbers in the same order)
+                bool refactor = true;
+                if (pass == 1) {
+                    if (mx > 1e-10) s_flag = 1;
+                    __syncthreads();
+                    refactor = s_flag != 0;
+                }
+                // ---- P -= Q_prev S on this chunk
+                for (int ib = 0; ib < nblk; ib++) {
+                    chunk_load(xq, p.Y + ib * TS_PB, p.ld, r0, rows, TS_PB, w, c);
+                    __syncthreads();
+                    chunk_stage(xq, Xt, w, c);
+                    __syncthreads();
+                    chunk_minus_times_matrix(xp, Xt, Ss + ib * TS_PB * CQ_GP, CQ_GP, w, c);
+                }
+                __syncthreads();
+                if (!refactor) {
+                    chunk_store(xp, P, p.ld, r0, rows, b, w, c);
+                    break;
+                }
+            }
+            // ---- the panel itself: CholeskyQR2, accepted pass by pass on the pivot test
+            bool done = false;
+            if (!p.force_householder && p.m >= b) {
+                bool ok = true;
+                for (int cp = 0; cp < 2 && ok; cp++) {
+                    chunk_stage(xp, Xt, w, c);
+                    __syncthreads();
+                    chunk_gram(xp, Xt, part, b, w, c, p.Gpart[cp] + (int64_t)chunk * TS_PB * CQ_GP);
+                    fused_sync<SYNC>();
+                    const bool good = cholqr_factor_body(p.Gpart[cp], p.nchunks, b, Ms, Gs);
+                    if (tid == 0) s_flag = good ? 1 : 0;
+                    __syncthreads();
+                    ok = s_flag != 0;
+                    if (ok) chunk_times_matrix(xp, Xt, Ms, CQ_GP, b, w, c, true);      // P <- P R^-1 (Xt still holds the panel)
+                    __syncthreads();
+                }
+                done = ok;
+            }
+            chunk_store(xp, P, p.ld, r0, rows, b, w, c);
+            if (done) continue;
+            // ---- Householder TSQR with explicit chunk factors, level by level (uniform branch: `done` is the same in every CTA)
+            __syncthreads();
+            int lrows[4], lchunks[4], nlevels = 0;
+            for (int rws = p.m; nlevels < 4;) {
+                lrows[nlevels] = rws; lchunks[nlevels] = (rws + TS_CH - 1) / TS_CH; nlevels++;
+                if (lchunks[nlevels - 1] == 1) break;
+                rws = lchunks[nlevels - 1] * b;
+            }
+            for (int l = 0; l < nlevels; l++) {
+                if (chunk < lchunks[l]) {
+                    double* M = l == 0 ? P : p.rst[l - 1];
+                    const int64_t mld = l == 0 ? p.ld : b;
+                    tsqr_factor_body(M, mld, lrows[l], b, p.rst[l], p.tau[l], fs, chunk);
+                    __syncthreads();
+                    tsqr_apply_body(M, mld, lrows[l], b, p.tau[l], nullptr, sm, chunk);
+                    __syncthreads();
+                }
+                fused_sync<SYNC>();
+            }
+            for (int l = nlevels - 2; l >= 0; l--) {
+                if (chunk < lchunks[l]) {
+                    double* M = l == 0 ? P : p.rst[l - 1];
+                    const int64_t mld = l == 0 ? p.ld : b;
+                    const int64_t rr0 = (int64_t)chunk * TS_CH;
+                    const int rrows = (int)((lrows[l] - rr0) < TS_CH ? (lrows[l] - rr0) : TS_CH);
+                    chunk_load(xq, M, mld, rr0, rrows, b, w, c);
+                    chunk_stage(xq, Xt, w, c);
+                    for (int e = tid; e < TS_PB * TS_PB; e += TS_CH) {
+                        const int i = e >> 5, k = e & 31;
+                        Ms[i * CQ_GP + k] = (i < b && k < b) ? p.rst[l][((int64_t)chunk * b + i) * b + k] : 0.0;
+                    }
+                    __syncthreads();
+                    chunk_times_matrix(xq, Xt, Ms, CQ_GP, b, w, c, false);
+                    chunk_store(xq, M, mld, rr0, rrows, b, w, c);
+                    __syncthreads();
+                }
+                fused_sync<SYNC>();
+            }
+        }
+    }
+}
+constexpr size_t fused_smem_bytes(int q) {
+    return (size_t)(TS_PB * CQ_XP + TS_NW * TS_PB * CQ_GP + 2 * TS_PB * CQ_GP + ((q + TS_PB - 1) / TS_PB) * TS_PB * CQ_GP) * sizeof(double);
 }
 
 namespace {
@@ -541,8 +731,64 @@ GemmDesc proj_update_desc(double* Y, int64_t ld, int64_t m, int j0, int b, const
 }
 }  // namespace
 
+namespace {
+bool fused_eligible(int64_t m, int q) {
+    if (m > FUSED_MAX_ROWS || q > FUSED_MAX_COLS || m < q) return false;
+    const char* e = getenv("ACETN_B200_ORTHO_FUSED");     // dev / test knob, read per call
+    return !(e != nullptr && e[0] == '0');
+}
+size_t fused_extra_doubles(int64_t m, int q) {
+    const size_t nch = (size_t)((m + TS_CH - 1) / TS_CH), nblk = (size_t)((q + TS_PB - 1) / TS_PB);
+    return nch * nblk * TS_PB * CQ_GP + 2 * nch * TS_PB * CQ_GP + 64;
+}
+
+int ortho_fused_launch(double* Y, int64_t m, int q, int64_t ld, double* scratch, double* extra, cudaStream_t s) {
+    OrthoFusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.Y = Y; p.ld = ld; p.m = (int)m; p.q = q;
+    p.nchunks = (int)((m + TS_CH - 1) / TS_CH);
+    const char* fh = getenv("ACETN_B200_TSQR_HOUSEHOLDER");
+    p.force_householder = fh != nullptr && fh[0] == '1';
+    const size_t nblk = (size_t)((q + TS_PB - 1) / TS_PB);
+    p.Spart = extra;
+    p.Gpart[0] = extra + (size_t)p.nchunks * nblk * TS_PB * CQ_GP;
+    p.Gpart[1] = p.Gpart[0] + (size_t)p.nchunks * TS_PB * CQ_GP;
+    Levels L = plan_levels(m, TS_PB);                       // pointer layout of tsqr_panel (sized for full panels)
+    AB_REQUIRE(L.n <= 4, "orthonormalize (fused): too many TSQR levels");
+    double* cur = scratch;
+    for (int l = 0; l < L.n; l++) {
+        p.rst[l] = cur; cur += (size_t)L.chunks[l] * TS_PB * TS_PB;
+        p.tau[l] = cur; cur += (size_t)L.chunks[l] * TS_PB + 64 - ((size_t)L.chunks[l] * TS_PB) % 2;
+    }
+    const size_t smem = fused_smem_bytes(q);
+    if (p.nchunks == 1) {
+        AB_ENSURE_SMEM(ortho_fused_kernel<0>, smem);
+        ortho_fused_kernel<0><<<1, TS_CH, smem, s>>>(p);
+        AB_LAUNCHED();
+    } else if (p.nchunks <= 8) {
+        AB_ENSURE_SMEM(ortho_fused_kernel<1>, smem);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)p.nchunks); cfg.blockDim = dim3(TS_CH); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.nchunks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        AB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ortho_fused_kernel<1>, p));
+        note_launch(1);
+    } else {
+        AB_ENSURE_SMEM(ortho_fused_kernel<2>, smem);
+        void* args[] = {&p};
+        AB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)ortho_fused_kernel<2>, dim3((unsigned)p.nchunks), dim3(TS_CH), args, smem, s));
+        note_launch(1);
+    }
+    return OK;
+}
+}  // namespace
+
 size_t orthonormalize_workspace_bytes(int64_t m, int q) {
     size_t bytes = ws_round(tsqr_scratch_doubles(m) * sizeof(double));
+    if (m <= FUSED_MAX_ROWS && q <= FUSED_MAX_COLS) bytes += ws_round(fused_extra_doubles(m, q) * sizeof(double));
     bytes += ws_round((size_t)q * TS_PB * sizeof(double)) + ws_round(16 * sizeof(int));
     size_t g = 0;
     for (int j0 = TS_PB; j0 < q; j0 += TS_PB) {
@@ -560,9 +806,11 @@ int orthonormalize_launch(double* Y, int64_t m, int q, int64_t ld, void* wsp, si
     AB_REQUIRE(m < 2147483647LL, "orthonormalize: m too large");
     Workspace ws(wsp, ws_bytes);
     double* scratch = ws.take<double>(tsqr_scratch_doubles(m));
+    double* extra = (m <= FUSED_MAX_ROWS && q <= FUSED_MAX_COLS) ? ws.take<double>(fused_extra_doubles(m, q)) : nullptr;
     double* Sc = ws.take<double>((size_t)q * TS_PB);
     int* flag = ws.take<int>(16);
     if (ws.overflow) { set_error("orthonormalize: workspace too small"); return ERR_WORKSPACE; }
+    if (extra != nullptr && fused_eligible(m, q)) return ortho_fused_launch(Y, m, q, ld, scratch, extra, s);
     void* gws = ws.base + ws.used;
     size_t gws_bytes = ws.bytes - ws.used;
     for (int j0 = 0; j0 < q; j0 += TS_PB) {

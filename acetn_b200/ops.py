@@ -72,11 +72,23 @@ def _stream(dev, stream=None):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_replayed_launches = 0
+
+
 def launch_count():
-    return int(_lib.load().acetn_b200_launch_count())
+    """Kernels of libacetn_b200.so launched so far: stream launches counted by the library + kernel nodes of replayed CUDA graphs."""
+    return int(_lib.load().acetn_b200_launch_count()) + _replayed_launches
+
+
+def note_replayed_launches(n):
+    """A CUDA graph holding `n` kernels of the library was replayed (renormalization.MoveGraph)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
 
 
 def reset_launch_count():
+    global _replayed_launches
+    _replayed_launches = 0
     _lib.load().acetn_b200_reset_launch_count()
 
 

@@ -398,11 +398,14 @@ class MoveGraph:
         torch.cuda.synchronize(dev)
         self._keep = None
         gc.disable()
+        n0 = ops.launch_count()
         try:
             with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
                 self.staged = self._enqueue(view)
         finally:
             gc.enable()
+        self.n_kernels = ops.launch_count() - n0      # kernel nodes of the library in the graph (recorded, not run)
+        ops.note_replayed_launches(-self.n_kernels)   # ... which the library counted as launches while they were being captured
         self._keep = None            # capture is over: the graph's private pool keeps the addresses of the intermediates
         self.replays = 0
 
@@ -462,6 +465,7 @@ class MoveGraph:
         for n, t in enumerate(self.tasks):                  # the reference's draws, in the reference's order
             self.omega[n].copy_(pc.draw_omega(view, t["plaq"], t["k"]))
         self.graph.replay()
+        ops.note_replayed_launches(self.n_kernels)
         if [int(v) for v in self.infos[:, 0].tolist()] != [self.chi] * len(self.tasks):      # the one host read of the phase
             return False
         for s2, k, c1, c2, e in self.staged:

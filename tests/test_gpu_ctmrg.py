@@ -21,7 +21,7 @@ from tests.util import cell_from_plain, load_golden, model_terms, rotated_qr
 pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
-    from acetn_b200 import linalg
+    from acetn_b200 import linalg, ops
     from acetn_b200.ipeps import CTMRGConfig, Ipeps, SiteTensor
     from acetn_b200.renormalization import DirectionalMover, ProjectorCalculator, ctmrg
 
@@ -328,10 +328,13 @@ def test_graph_replay_is_bit_identical(nx, ny, D, chi, paired, monkeypatch):
         torch.manual_seed(5)
         ip = Ipeps.from_plain(cell, CTMRGConfig(steps=6))
         mover = DirectionalMover(ip.ctmrg_config)
+        ops.reset_launch_count()
         ctmrg(ip, ip.ctmrg_config, mover)
         torch.cuda.synchronize()
-        out[mode] = (ip, mover.graph_replays)
+        out[mode] = (ip, mover.graph_replays, ops.launch_count())
     assert out["0"][1] == 0 and out["auto"][1] > 0
+    # kernels inside replayed graphs count as launches of the library (bench.py's gpu_launches): same work, same count +- the warm-up
+    assert 0.9 * out["0"][2] <= out["auto"][2] <= 1.6 * out["0"][2], (out["0"][2], out["auto"][2])
     a, b = out["0"][0], out["auto"][0]
     for s in a.site_list:
         for k in range(4):

@@ -113,8 +113,14 @@ def test_gemm_epilogue_paired_and_scalar_stores():
 
 
 # ---------------------------------------------------------------------------------------------- K4 TSQR
-@pytest.mark.parametrize("m,q", [(300, 20), (1000, 64), (4097, 130), (16384, 258), (80, 22), (40, 40), (257, 33)])
-def test_orthonormalize_random(m, q):
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("m,q", [(300, 20), (1000, 64), (4097, 130), (16384, 258), (80, 22), (40, 40), (257, 33), (1024, 66), (4096, 130),
+                                 (1296, 38), (513, 97)])
+def test_orthonormalize_random(m, q, fused, monkeypatch):
+    """K4 on both of its launch forms: the single cooperative kernel for small matrices (m <= 4096, q <= 130) and the multi-launch path."""
+    if fused == "0" and (m > 4096 or q > 130):
+        pytest.skip("only the multi-launch path exists at this size (covered by fused='1')")
+    monkeypatch.setenv("ACETN_B200_ORTHO_FUSED", fused)
     Y0 = rnd(m, q, seed=20)
     Q = ops.orthonormalize(Y0.clone())
     eye = torch.eye(q, dtype=torch.float64, device=DEV)
@@ -122,26 +128,57 @@ def test_orthonormalize_random(m, q):
     assert rel(Q @ (Q.T @ Y0), Y0) < 1e-13
 
 
-@pytest.mark.parametrize("kind", ["graded", "rank_deficient"])
-def test_orthonormalize_ill_conditioned(kind):
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("householder", ["0", "1"])
+@pytest.mark.parametrize("kind", ["graded", "rank_deficient", "graded_columns"])
+def test_orthonormalize_ill_conditioned(kind, householder, fused, monkeypatch):
+    """Graded spectrum over 20 decades, exact rank deficiency, columns scaled over 30 decades: the pivot test of the CholeskyQR2 fast
+    path must hand such panels to the Householder TSQR (fused kernel and multi-launch path alike); `householder=1` forces it."""
+    monkeypatch.setenv("ACETN_B200_ORTHO_FUSED", fused)
+    monkeypatch.setenv("ACETN_B200_TSQR_HOUSEHOLDER", householder)
     m, q = 2048, 96
     U = torch.linalg.qr(rnd(m, q, seed=21)).Q
     V = torch.linalg.qr(rnd(q, q, seed=22)).Q
     if kind == "graded":
         s = torch.logspace(0, -20, q, dtype=torch.float64, device=DEV)
-    else:
+        Y0 = (U * s) @ V.T
+    elif kind == "rank_deficient":
         s = torch.cat([torch.ones(10, dtype=torch.float64, device=DEV), torch.zeros(q - 10, dtype=torch.float64, device=DEV)])
-    Y0 = (U * s) @ V.T
+        Y0 = (U * s) @ V.T
+    else:
+        Y0 = rnd(m, q, seed=23) * torch.logspace(0, -30, q, dtype=torch.float64, device=DEV)
     Q = ops.orthonormalize(Y0.clone())
     eye = torch.eye(q, dtype=torch.float64, device=DEV)
     assert float((Q.T @ Q - eye).abs().max()) < 1e-13
-    assert float((Q @ (Q.T @ Y0) - Y0).norm() / Y0.norm()) < 1e-13
+    if kind == "graded_columns":
+        # every column of Y0 must lie in span(Q) relative to ITS OWN norm (a scaled column is as good a direction as any other)
+        R = Y0 - Q @ (Q.T @ Y0)
+        assert float((R.norm(dim=0) / Y0.norm(dim=0)).max()) < 1e-12
+    else:
+        assert float((Q @ (Q.T @ Y0) - Y0).norm() / Y0.norm()) < 1e-13
+
+
+@pytest.mark.parametrize("m,q", [(1024, 66), (80, 22), (2500, 128)])
+def test_orthonormalize_fused_matches_multi_launch(m, q, monkeypatch):
+    """Same algorithm, same per-chunk arithmetic: the fused kernel's basis equals the multi-launch path's up to the rounding of the
+    inter-panel projections (FMA chunk code vs K1), far inside the rSVD's tolerance."""
+    Y0 = rnd(m, q, seed=31)
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("ACETN_B200_ORTHO_FUSED", fused)
+        out[fused] = ops.orthonormalize(Y0.clone())
+    assert float((out["0"] - out["1"]).abs().max()) < 1e-12
 
 
 # ---------------------------------------------------------------------------------------------- K5 Jacobi
-@pytest.mark.parametrize("q", [1, 2, 5, 22, 64, 129, 258])
-def test_jacobi_svd(q):
-    # the core handed to K5 is the triangular factor of a QR (acetn_b200 rsvd pipeline); condition number 1e9
+@pytest.mark.parametrize("small", ["1", "0"])
+@pytest.mark.parametrize("q", [1, 2, 5, 22, 37, 64, 66, 111, 112, 113, 129, 258])
+def test_jacobi_svd(q, small, monkeypatch):
+    # the core handed to K5 is the triangular factor of a QR (acetn_b200 rsvd pipeline); condition number 1e9.  Cores up to q = 112 run
+    # in the single-CTA kernel (jacobi_small_kernel), larger ones in the multi-CTA block kernel; small="0" forces the latter.
+    if small == "0" and q > 112:
+        pytest.skip("covered by small='1' (the block kernel is the only one at this size)")
+    monkeypatch.setenv("ACETN_B200_JACOBI_SMALL", small)
     G = rnd(q, q, seed=30) * torch.logspace(0, -9, q, dtype=torch.float64, device=DEV)[None, :]
     R = torch.linalg.qr(G.cpu()).R.to(DEV).contiguous()
     S, Wt, Jt, info = ops.jacobi_svd(R)
@@ -155,8 +192,26 @@ def test_jacobi_svd(q):
     assert 0 < int(info[1]) <= 15
 
 
-def test_jacobi_svd_dense_unpreconditioned():
+def test_jacobi_svd_rank_deficient_and_truncation_count(monkeypatch):
+    """Zero singular values (exactly rank-deficient core, as on product-state boundaries) and the truncation count s/s0 > cutoff on
+    both kernels."""
+    q = 48
+    g = torch.Generator().manual_seed(33)
+    A = torch.randn(q, 10, dtype=torch.float64, generator=g) @ torch.randn(10, q, dtype=torch.float64, generator=g)
+    R = torch.linalg.qr(A).R.to(DEV).contiguous()
+    ref = torch.linalg.svdvals(R.cpu()).to(DEV)
+    for small in ("1", "0"):
+        monkeypatch.setenv("ACETN_B200_JACOBI_SMALL", small)
+        S, Wt, Jt, info = ops.jacobi_svd(R, chi=40, cutoff=1e-10)
+        assert float((S - ref).abs().max() / ref[0]) < 5e-14
+        assert int(info[0]) == 10
+        assert rel(Jt.T @ torch.diag(S) @ Wt, R) < 1e-13
+
+
+@pytest.mark.parametrize("small", ["1", "0"])
+def test_jacobi_svd_dense_unpreconditioned(small, monkeypatch):
     """A dense core that is not QR-preconditioned needs more sweeps but must still converge."""
+    monkeypatch.setenv("ACETN_B200_JACOBI_SMALL", small)
     q = 64
     R = rnd(q, q, seed=31) * torch.logspace(0, -6, q, dtype=torch.float64, device=DEV)[None, :]
     S, Wt, Jt, info = ops.jacobi_svd(R)
@@ -298,12 +353,12 @@ def test_gemm_fuzz_two_level_descriptors(seed):
 
 
 @pytest.mark.parametrize("cond", [1e1, 1e3, 1e5, 1e7, 1e12])
-def test_orthonormalize_fast_path_matches_householder_quality(cond, monkeypatch):
+@pytest.mark.parametrize("m,q", [(8192, 96), (2048, 96)])
+def test_orthonormalize_fast_path_matches_householder_quality(cond, m, q, monkeypatch):
     """K4's CholeskyQR2 fast path (taken per 32-column panel when every Cholesky pivot keeps > 1e-11 of its diagonal) against the
     Householder TSQR path on tall matrices of prescribed condition number: orthogonality at machine precision on both, and the
     basis must capture every left singular direction u_k of Y as well as the Householder basis does (the residual of u_k outside
     span(Q), weighted by s_k / s_0 -- what the rSVD's spectrum sees -- stays at 1e-14)."""
-    m, q = 8192, 96
     g = torch.Generator().manual_seed(17)
     U = torch.linalg.qr(torch.randn(m, q, dtype=torch.float64, generator=g)).Q.cuda()
     V = torch.linalg.qr(torch.randn(q, q, dtype=torch.float64, generator=g)).Q.cuda()
