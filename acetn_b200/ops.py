@@ -1,5 +1,6 @@
 """Tensor-level wrappers around the C ABI: allocate outputs/workspace with torch, pass raw pointers, extents,
 strides and the current CUDA stream.  No torch types cross the boundary."""
+import contextlib
 import ctypes
 
 import torch
@@ -31,11 +32,35 @@ def require_cuda_device(device):
         raise RuntimeError("acetn_b200: tensors must live on a CUDA (B200) device; there is no CPU path for backend='b200'")
 
 
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _dev_index(dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _on(dev):
+    """Context that makes `dev` the current CUDA device for the C call -- a no-op object when it already is (the common case: the
+    torch.cuda.device context manager costs ~10 us, a third of the host time of a launch-bound sweep went into it and current_stream)."""
+    idx = dev.index
+    if idx is None or torch.cuda.current_device() == idx:
+        return _NULL_CTX
+    return torch.cuda.device(idx)
+
+
+def _raw_stream(dev):
+    """cudaStream_t (int) of torch's current stream on `dev`."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(_dev_index(dev))
+    except AttributeError:      # private torch API not available: the public (slower) route
+        return torch.cuda.current_stream(dev).cuda_stream
+
+
 def _ws(dev, nbytes, stream=None):
     """Per-(device, stream) grow-only scratch buffer (torch-allocated; the library owns no device memory)."""
     # one scratch buffer per CUDA stream: work enqueued on different streams may run concurrently
-    sid = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), sid)
+    sid = stream.cuda_stream if stream is not None else _raw_stream(dev)
+    key = (dev.type, _dev_index(dev), sid)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
@@ -69,7 +94,7 @@ def _stream(dev, stream=None):
     """cudaStream_t handed to the library: an explicit side stream, or torch's current stream."""
     if stream is not None:
         return ctypes.c_void_p(stream.cuda_stream)
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    return ctypes.c_void_p(_raw_stream(dev))
 
 
 _replayed_launches = 0
@@ -100,7 +125,7 @@ def gemm_ex(M, N, K, batch, A, B, C, idx, alpha=1.0, beta=0.0, force_tile=0, for
     ix = _lib.i64_array(idx)
     nb = lib.acetn_b200_gemm_workspace_bytes(M, N, K, batch, ix, force_tile, force_splitk)
     ws = _ws(dev, nb)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_gemm(M, N, K, batch, _p(A), _p(B), _p(C), ix, float(alpha), float(beta), force_tile, force_splitk,
                                  _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "gemm")
@@ -153,13 +178,13 @@ def quarter_tensor(C, E2, E1, A_view, normalize=True, stream=None, absmax=None, 
     if enc_storage is not None:
         if normalize:
             raise ValueError("quarter_tensor: the K7 encoding is taken from the un-normalised tensor (normalize=False)")
-        with torch.cuda.device(dev):
+        with _on(dev):
             st = lib.acetn_b200_quarter_tensor_enc(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
                                                    _p(Q), _p(absmax) if absmax is not None else None, _p(enc_storage), enc_storage.numel(),
                                                    _p(ws), ws.numel(), _stream(dev, stream))
         _lib.check(st, "quarter_tensor_enc")
         return Q, (xc, D, D, xe, D, D), I8Encoded(enc_storage, Q.shape[0], Q.shape[1])
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_quarter_tensor(_p(C), _p(E2), _p(E1), _p(A_view), _lib.i64_array(A_view.stride()), xa, xb, xc, xe, D, d,
                                            1 if normalize else 0, _p(Q), _p(absmax) if absmax is not None else None, _p(ws), ws.numel(),
                                            _stream(dev, stream))
@@ -175,7 +200,7 @@ def orthonormalize(Y):
     lib = _lib.load()
     nb = lib.acetn_b200_orthonormalize_workspace_bytes(m, q)
     ws = _ws(dev, nb)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_orthonormalize(_p(Y), m, q, q, _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "orthonormalize")
     return Y
@@ -193,7 +218,7 @@ def jacobi_svd(R, chi=None, cutoff=0.0):
     info = torch.zeros(2, dtype=torch.int32, device=dev)
     nb = lib.acetn_b200_jacobi_svd_workspace_bytes(q)
     ws = _ws(dev, nb)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_jacobi_svd(_p(R), q, _p(S), _p(Wt), _p(Jt), q if chi is None else chi, float(cutoff), _p(info),
                                        _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "jacobi_svd")
@@ -233,7 +258,7 @@ def rsvd(mats, omega, niter=2, reorth_adjoint=False, chi=None, cutoff=1e-12, str
     ws = _ws(dev, nb, stream)
     ptrs = (ctypes.c_void_p * nmat)(*[t.data_ptr() if t is not None else None for t in mats])
     eptrs = (ctypes.c_void_p * nmat)(*[e.storage.data_ptr() if e is not None else None for e in encs])
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_rsvd_enc(nmat, ptrs, eptrs, r_arr, c_arr, _p(omega), q, int(niter), 1 if reorth_adjoint else 0,
                                      q if chi is None else int(chi), float(cutoff), _p(U) if want_u else None, _p(S), _p(V), _p(info),
                                      _p(AtQ) if want_atq else None, _p(Wt) if want_atq else None, _p(ws), ws.numel(),
@@ -261,7 +286,7 @@ def projectors_from_usv(Q1, Q4, U, V, S, keep, stream=None, qmax1=None, qmax4=No
     def ptr(t):
         return _p(t) if t is not None else None
 
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_projectors_from_usv_enc(ptr(Q1), ptr(enc1.storage) if enc1 is not None else None, m1, n1,
                                                     ptr(Q4), ptr(enc4.storage) if enc4 is not None else None, m4, n4,
                                                     ptr(U), U.stride(0) if U is not None else 0, _p(V), V.stride(0), _p(S), keep,
@@ -282,7 +307,7 @@ def absorb_corner1(ci, ei, proj):
     lib = _lib.load()
     out = torch.empty(xa, xx, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_absorb_corner_workspace_bytes(xa, xb, xc, xx, D))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_absorb_corner1(_p(ci), _p(ei), _p(proj), xa, xb, xc, xx, D, _p(out), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_corner1")
     return out
@@ -300,7 +325,7 @@ def absorb_corner2(ci, ei, proj):
     lib = _lib.load()
     out = torch.empty(xx, xc, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_absorb_corner_workspace_bytes(xa, xb, xc, xx, D))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_absorb_corner2(_p(ci), _p(ei), _p(proj), xa, xb, xc, xx, D, _p(out), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_corner2")
     return out
@@ -318,7 +343,7 @@ def absorb_edge(ei, A_view, proj2, proj1, normalize=True):
     lib = _lib.load()
     out = torch.empty(xy, xx, D, D, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_absorb_edge_workspace_bytes(xa, xb, xx, xy, D, d))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_absorb_edge(_p(ei), _p(A_view), _lib.i64_array(A_view.stride()), _p(proj2), _p(proj1), xa, xb, xx, xy, D, d,
                                         1 if normalize else 0, _p(out), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_edge")
@@ -337,7 +362,7 @@ def absorb_edge_begin(ei, A_view, proj1):
     lib = _lib.load()
     T3 = torch.empty(xa * D * D, xx * D * D, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_absorb_edge_begin_workspace_bytes(xa, xb, xx, D, d))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_absorb_edge_begin(_p(ei), _p(A_view), _lib.i64_array(A_view.stride()), _p(proj1), xa, xb, xx, D, d, _p(T3),
                                               _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "absorb_edge_begin")
@@ -355,7 +380,7 @@ def absorb_edge_finish(T3, proj2, D, normalize=True):
     lib = _lib.load()
     out = torch.empty(xy, xx, D, D, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_absorb_edge_finish_workspace_bytes(xa, xx, xy, D))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_absorb_edge_finish(_p(proj2), _p(T3), xa, xx, xy, D, 1 if normalize else 0, _p(out), _p(ws), ws.numel(),
                                                _stream(dev))
     _lib.check(st, "absorb_edge_finish")
@@ -376,7 +401,7 @@ def permute_copy(view):
     strides = [st for s, st in zip(view.shape, view.stride()) if s != 1] or [1]
     if len(dims) > 8:
         raise RuntimeError("permute_copy: more than 8 non-trivial dims")
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _lib.load().acetn_b200_permute(_p(out), _p(view), len(dims), _lib.i64_array(dims), _lib.i64_array(strides), _stream(dev))
     _lib.check(st, "permute")
     return out
@@ -446,7 +471,7 @@ def site_rdm(C, E, A):
     lib = _lib.load()
     rho = torch.empty(d, d, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_site_rdm_workspace_bytes(chi, D, d))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_site_rdm(_p(C[0]), _p(C[1]), _p(C[2]), _p(C[3]), _p(E[0]), _p(E[1]), _p(E[2]), _p(E[3]), _p(A),
                                      _lib.i64_array(A.stride()), chi, D, d, _p(rho), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "site_rdm")
@@ -471,7 +496,7 @@ def bond_rdm(site1, site2, k):
     lib = _lib.load()
     rho = torch.empty(d, d, d, d, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_bond_rdm_workspace_bytes(chi, D, d))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_bond_rdm(_p(bt[0]), _p(bt[1]), _p(bt[2]), _p(bt[3]), _p(bt[4]), _p(a1), _lib.i64_array(a1.stride()),
                                      _p(bt[5]), _p(bt[6]), _p(bt[7]), _p(bt[8]), _p(bt[9]), _p(a2), _lib.i64_array(a2.stride()),
                                      chi, D, d, _p(rho), _p(ws), ws.numel(), _stream(dev))
@@ -490,7 +515,7 @@ def norm_tensor(site1, site2, k, a1q, a2q):
     lib = _lib.load()
     n12 = torch.empty(nD, nD, nD, nD, dtype=torch.float64, device=dev)
     ws = _ws(dev, lib.acetn_b200_norm_tensor_workspace_bytes(chi, D, nD))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_norm_tensor(_p(bt[0]), _p(bt[1]), _p(bt[2]), _p(bt[3]), _p(bt[4]), _p(a1q), _p(bt[5]), _p(bt[6]), _p(bt[7]),
                                         _p(bt[8]), _p(bt[9]), _p(a2q), chi, D, nD, _p(n12), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "norm_tensor")
@@ -501,7 +526,7 @@ def absmax(x, out):
     """out[0] = max(out[0], max|x|)  (out: 1-element device tensor, zero it first)."""
     dev = _require_cuda(x, out)
     x = x.contiguous()
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _lib.load().acetn_b200_absmax(_p(x), x.numel(), _p(out), _stream(dev))
     _lib.check(st, "absmax")
     return out
@@ -512,7 +537,7 @@ def frob_normalize(x):
     dev = _require_cuda(x)
     assert x.is_contiguous()
     ws = _ws(dev, 8192 * 8)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _lib.load().acetn_b200_frob_normalize(_p(x), x.numel(), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "frob_normalize")
     return x
@@ -529,7 +554,7 @@ def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
     lib = _lib.load()
     info = torch.zeros(2, dtype=torch.int32, device=dev)
     ws = _ws(dev, lib.acetn_b200_als_workspace_bytes(nD, bD, pD))
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_als_solve(_p(a1), _p(a2), _p(n12g), _p(n12), _p(a12g), nD, bD, pD, int(niter), float(tol), float(epsilon),
                                       _p(info), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "als_solve")
@@ -561,7 +586,7 @@ def i8_encode(Q, stream=None, storage=None):
     nb = lib.acetn_b200_i8_encoded_bytes(rows, cols)
     if storage is None or storage.numel() < nb:
         storage = torch.empty(nb, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_i8_encode(_p(Q), rows, cols, Q.stride(0), _p(storage), storage.numel(), _stream(dev, stream))
     _lib.check(st, "i8_encode")
     return I8Encoded(storage, rows, cols)
@@ -580,7 +605,7 @@ def i8_matmul(enc, Y, adjoint=False, stream=None, out=None):
         out = torch.empty(m, q, dtype=torch.float64, device=dev)
     nb = lib.acetn_b200_i8_matmul_workspace_bytes(enc.rows, enc.cols, q)
     ws = _ws(dev, nb, stream)
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = lib.acetn_b200_i8_matmul(_p(enc.storage), enc.rows, enc.cols, 1 if adjoint else 0, _p(Y), q, q, _p(out), out.stride(0),
                                       _p(ws), ws.numel(), _stream(dev, stream))
     _lib.check(st, "i8_matmul")
