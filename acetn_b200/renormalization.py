@@ -418,12 +418,15 @@ class MoveGraph:
         side = [st for st in mover._side_streams(self.device) if st is not None] or [main]
         keep, staged = [], []
         n = 0
+        used = []
+        proj = []
+        # every projector task of the phase forks off first (the moves of a paired phase are independent: all of them read the
+        # pre-phase state and the commit happens after the replay), one join, then every absorption
         for g in self.groups:
             p1, p2 = {}, {}
-            used = []
             for t in g:
                 st = side[n % len(side)]
-                if st is not main:
+                if st is not main and st not in used:
                     st.wait_stream(main)
                     used.append(st)
                 with torch.cuda.stream(st):
@@ -432,13 +435,16 @@ class MoveGraph:
                     p1[t["key"]], p2[t["key"]] = pc.finish_static(pend, chi)
                 keep.append(pend)
                 n += 1
-            for st in used:
-                main.wait_stream(st)
-            used = []
-            for i, t in enumerate(g):
+            proj.append((p1, p2))
+        for st in used:
+            main.wait_stream(st)
+        used = []
+        i = 0
+        for g, (p1, p2) in zip(self.groups, proj):
+            for t in g:
                 k, src = t["k"], view[t["s1"]]
                 st = side[i % len(side)]
-                if st is not main:
+                if st is not main and st not in used:
                     st.wait_stream(main)
                     used.append(st)
                 with torch.cuda.stream(st):
@@ -446,9 +452,10 @@ class MoveGraph:
                     c2 = mover.renormalize_cj2(src['C'][k], src['E'][k], p2[t["j"]])
                     e = mover.renormalize_ej(src['E'][(3 + k) % 4], src.bond_permute(k), p2[t["i"]], p1[t["j"]])
                 staged.append((t["s2"], k, c1, c2, e))
-            for st in used:
-                main.wait_stream(st)
-            keep.append((p1, p2))
+                i += 1
+        for st in used:
+            main.wait_stream(st)
+        keep.append(proj)
         self._keep = keep
         return staged
 
@@ -546,10 +553,11 @@ class DirectionalMover:
         self._slots = []
         self._graphs, self._graph_ok, self._arena = {}, {}, {}
 
-    # chi * D^2 up to which a phase is replayed as a CUDA graph ("auto").  Measured (tools/small_config_bench.py, 2x2 cell): D=2 chi=20
-    # (chi D^2 = 80) 134 -> 166 sweeps/s; D=4 chi=64 (1024) 45.5 -> 40.6: there the eager schedule's piecewise absorptions and stream
-    # priorities are worth more than the saved launch overhead -- the dependent-kernel latency, not the launch, bounds both
-    GRAPH_MAX_DIM = 256
+    # chi * D^2 up to which a phase is replayed as a CUDA graph ("auto").  Measured (tools/small_config_bench.py / bench.py, 2x2 cell,
+    # eager -> graph, after all tasks of a paired phase fork as parallel branches): D=2 chi=20 (chi D^2 = 80) 149 -> 312 sweeps/s,
+    # D=4 chi=64 (1024) 76 -> 83, D=6 chi=36 (1296) 87 -> 103, D=5 chi=80 (2000) 42.3 -> 42.9, D=6 chi=64 (2304) 41.3 -> 42.2,
+    # D=8 chi=48 (3072) 36.6 -> 38.8.  From 4096 on the thin products move to K7 and the sweep is throughput-bound: eager schedule.
+    GRAPH_MAX_DIM = 3072
 
     def arena_site(self, ipeps, site):
         """The fixed-address buffers of `site` (created from its current, saturated tensors; rebuilt when a shape changed, which
