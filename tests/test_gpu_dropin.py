@@ -79,16 +79,21 @@ def test_readme_quickstart_on_b200():
     Ipeps = setup()
     base = {"dtype": "float64", "device": "cuda", "TN": {"nx": 2, "ny": 2, "dims": {"phys": 2, "bond": 2, "chi": 20}},
             "model": {"name": "heisenberg", "params": {"J": 1.0}}}
-    res, calls = {}, {}
+    import time
+    res, calls, secs = {}, {}, {}
     for b200 in (False, True):
         torch.manual_seed(0)
         ip = Ipeps(_cuda_cfg(base, b200))
         ops.reset_launch_count()
         with MoveCounter() as ref_moves:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             ip.evolve(dtau=0.01, steps=100)
+            torch.cuda.synchronize()
+            secs[b200] = time.perf_counter() - t0
             res[b200] = {k: float(v) for k, v in ip.measure().items()}
         calls[b200] = (ref_moves.calls, ops.launch_count())
-    print("quickstart torch:", res[False], "b200:", res[True], "calls:", calls)
+    print("quickstart torch:", res[False], "b200:", res[True], "calls:", calls, "evolve seconds (incl. first-use warm-up):", secs)
     assert calls[False][0] > 0 and calls[False][1] == 0
     assert calls[True][0] == 0 and calls[True][1] > 0
     assert res[True]["Energy"] == pytest.approx(res[False]["Energy"], abs=1e-6)
