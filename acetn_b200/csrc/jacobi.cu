@@ -16,6 +16,7 @@ namespace cg = cooperative_groups;
 namespace ab200 {
 
 constexpr int JB_THREADS = 256;   // 8 warps: one warp per row pair of a local step (br <= 8)
+constexpr int JB_NIT = 5;         // double2 per lane and row held in registers by the cached rotation (rows up to 320 columns)
 
 struct JacobiParams {
     double* X;      // n x ld, row major (n = nb * br rows, zero padded)
@@ -28,6 +29,80 @@ struct JacobiParams {
     double* conv;   // [max_sweeps] max relative off-diagonal seen in each sweep
     int* info;      // [0] sweeps used
 };
+
+// Rotation that orthogonalises two rows from their Gram entries, without sqrt or division: two dependent rsqrt instead of
+// sqrt -> division -> rsqrt (this scalar chain is the critical path of every Jacobi step).
+//   cos^2 = (1 + |d| / h) / 2,  sin = sgn(d) s_ab / (h cos),  d = s_bb - s_aa,  h = sqrt(d^2 + 4 s_ab^2)
+// (the same rotation as t = sgn(d) 2 s_ab / (|d| + h), cos = 1 / sqrt(1 + t^2), sin = cos t.)
+__device__ __forceinline__ void rotation_from_gram(double saa, double sbb, double sab, double& cs, double& sn) {
+    const double d = sbb - saa;
+    const double rh = rsqrt(fma(d, d, 4.0 * sab * sab));
+    const double c2 = fma(0.5 * fabs(d), rh, 0.5);
+    const double rc = rsqrt(c2);
+    cs = c2 * rc;
+    sn = (d >= 0.0 ? sab : -sab) * rh * rc;
+}
+
+// One row pair, owned by a group of G lanes (G = 32: a warp; smaller groups share a warp and own different pairs).  The X rows are
+// read ONCE into registers (NIT double2 per lane and row), the J rows are requested before the reduction + scalar chain and consumed
+// after it (CACHE_J), so a step is one shared-memory round trip, the dot products, log2(G) shuffle rounds, two rsqrt and the
+// rotation FMAs -- instead of two passes over shared memory around a sqrt / division / rsqrt chain.  Needs ncols2 <= G * NIT.
+template <int G, int NIT, bool CACHE_J>
+__device__ __forceinline__ int rotate_pair_cached(double* xa, double* xb, double* ja, double* jb, int ncols2, double tol, int gl) {
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (threadIdx.x & ((32 - G) & 31)));
+    double2* xa2 = reinterpret_cast<double2*>(xa);
+    double2* xb2 = reinterpret_cast<double2*>(xb);
+    double2* ja2 = reinterpret_cast<double2*>(ja);
+    double2* jb2 = reinterpret_cast<double2*>(jb);
+    double2 u[NIT], v[NIT], ju[CACHE_J ? NIT : 1], jv[CACHE_J ? NIT : 1];
+#pragma unroll
+    for (int i = 0; i < NIT; i++) {
+        const int c = gl + i * G;
+        const bool ok = c < ncols2;
+        u[i] = ok ? xa2[c] : make_double2(0.0, 0.0);
+        v[i] = ok ? xb2[c] : make_double2(0.0, 0.0);
+    }
+    if (CACHE_J) {
+#pragma unroll
+        for (int i = 0; i < NIT; i++) {
+            const int c = gl + i * G;
+            const bool ok = c < ncols2;
+            ju[i] = ok ? ja2[c] : make_double2(0.0, 0.0);
+            jv[i] = ok ? jb2[c] : make_double2(0.0, 0.0);
+        }
+    }
+    double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+    for (int i = 0; i < NIT; i++) {
+        saa = fma(u[i].x, u[i].x, fma(u[i].y, u[i].y, saa));
+        sbb = fma(v[i].x, v[i].x, fma(v[i].y, v[i].y, sbb));
+        sab = fma(u[i].x, v[i].x, fma(u[i].y, v[i].y, sab));
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        saa += __shfl_xor_sync(gmask, saa, o);
+        sbb += __shfl_xor_sync(gmask, sbb, o);
+        sab += __shfl_xor_sync(gmask, sab, o);
+    }
+    if (saa == 0.0 || sbb == 0.0) return 0;
+    // relative criterion |xa.xb| <= tol |xa||xb| tested without sqrt/div
+    if (sab * sab <= tol * tol * (saa * sbb)) return 0;
+    double cs, sn;
+    rotation_from_gram(saa, sbb, sab, cs, sn);
+#pragma unroll
+    for (int i = 0; i < NIT; i++) {
+        const int c = gl + i * G;
+        if (c < ncols2) {
+            double2 r;
+            r.x = cs * u[i].x - sn * v[i].x; r.y = cs * u[i].y - sn * v[i].y; xa2[c] = r;
+            r.x = sn * u[i].x + cs * v[i].x; r.y = sn * u[i].y + cs * v[i].y; xb2[c] = r;
+            const double2 a = CACHE_J ? ju[i] : ja2[c], b = CACHE_J ? jv[i] : jb2[c];
+            r.x = cs * a.x - sn * b.x; r.y = cs * a.y - sn * b.y; ja2[c] = r;
+            r.x = sn * a.x + cs * b.x; r.y = sn * a.y + cs * b.y; jb2[c] = r;
+        }
+    }
+    return 1;
+}
 
 // Rotate rows (xa, xb) of X (and ja, jb of J) held in shared memory so that xa . xb = 0.  One warp; rows are read
 // as double2 (the row pitch is even and the pad column, if any, is zero in X and J).
@@ -83,6 +158,10 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
     const int npairs = nb / 2, nbm1 = nb - 1;
     double* Xs = sm;                       // [2*br][ld]
     double* Js = sm + (size_t)2 * br * ld;
+    // rows of up to 320 columns (the rSVD cores of every BASELINE config) are rotated out of registers
+    const bool cached = ncols2 <= 32 * JB_NIT;
+#define JB_ROTATE(xa, xb, ja, jb) \
+    (cached ? (double)rotate_pair_cached<32, JB_NIT, true>(xa, xb, ja, jb, ncols2, p.tol, lane) : rotate_pair(xa, xb, ja, jb, ncols2, p.tol, lane))
 
     int sweep = 0;
     for (; sweep < p.max_sweeps; sweep++) {
@@ -115,7 +194,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
                             if (i == 0) { a = brm1; b = t; }
                             else { a = (t + i) % brm1; b = (t - i + brm1) % brm1; }
                             a += blk * br; b += blk * br;
-                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, lane);
+                            double rel = JB_ROTATE(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld);
                             worst = fmax(worst, rel);
                         }
                         __syncthreads();
@@ -124,7 +203,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
                     for (int t = 0; t < br; t++) {
                         if (warp < br) {
                             int a = warp, b = br + (warp + t) % br;
-                            double rel = rotate_pair(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, lane);
+                            double rel = JB_ROTATE(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld);
                             worst = fmax(worst, rel);
                         }
                         __syncthreads();
@@ -146,6 +225,7 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jacobi_block_kernel(JacobiParam
         if (wv <= p.tol) { sweep++; break; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) p.info[0] = sweep;
+#undef JB_ROTATE
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -160,6 +240,7 @@ constexpr int JS_GROUP = 8;      // lanes per row pair.  FP64 warp instructions 
                                  // scalar rotation chain (sqrt, division, rsqrt: ~60 of them) is per pair: four pairs per warp instead of two
                                  // halve the instruction stream of a step; with 16 lanes per pair the step was bound by the SM's FP64 issue rate
 constexpr int JS_MAX_Q = 112;
+constexpr int JS_NIT = (JS_MAX_Q / 2 + JS_GROUP - 1) / JS_GROUP;   // double2 per lane and row (X rows rotate out of registers)
 
 struct JacobiSmallParams {
     const double* R;     // q x q, row major
@@ -171,43 +252,6 @@ struct JacobiSmallParams {
     double* Jt;          // [q][q]
     int* count;          // [0] kept rank, [1] sweeps used
 };
-
-__device__ __forceinline__ int rotate_pair_group(double* xa, double* xb, double* ja, double* jb, int ncols2, double tol, int gl) {
-    // the groups of a warp own different pairs (or none): shuffles name only the lanes of this group
-    const unsigned gmask = ((1u << JS_GROUP) - 1u) << (threadIdx.x & (32 - JS_GROUP));
-    double2* xa2 = reinterpret_cast<double2*>(xa);
-    double2* xb2 = reinterpret_cast<double2*>(xb);
-    double saa = 0.0, sbb = 0.0, sab = 0.0;
-    for (int c = gl; c < ncols2; c += JS_GROUP) {
-        double2 u = xa2[c], v = xb2[c];
-        saa += u.x * u.x + u.y * u.y; sbb += v.x * v.x + v.y * v.y; sab += u.x * v.x + u.y * v.y;
-    }
-#pragma unroll
-    for (int o = JS_GROUP / 2; o > 0; o >>= 1) {
-        saa += __shfl_xor_sync(gmask, saa, o);
-        sbb += __shfl_xor_sync(gmask, sbb, o);
-        sab += __shfl_xor_sync(gmask, sab, o);
-    }
-    if (saa == 0.0 || sbb == 0.0) return 0;
-    const double r2 = sab * sab, den = saa * sbb;
-    if (r2 <= tol * tol * den) return 0;
-    const double d = sbb - saa;
-    const double h = sqrt(d * d + 4.0 * r2);
-    double t = (2.0 * sab) / (fabs(d) + h);
-    t = d >= 0.0 ? t : -t;
-    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-    double2* ja2 = reinterpret_cast<double2*>(ja);
-    double2* jb2 = reinterpret_cast<double2*>(jb);
-    for (int c = gl; c < ncols2; c += JS_GROUP) {
-        double2 u = xa2[c], v = xb2[c], r;
-        r.x = cs * u.x - sn * v.x; r.y = cs * u.y - sn * v.y; xa2[c] = r;
-        r.x = sn * u.x + cs * v.x; r.y = sn * u.y + cs * v.y; xb2[c] = r;
-        double2 ju = ja2[c], jv = jb2[c];
-        r.x = cs * ju.x - sn * jv.x; r.y = cs * ju.y - sn * jv.y; ja2[c] = r;
-        r.x = sn * ju.x + cs * jv.x; r.y = sn * ju.y + cs * jv.y; jb2[c] = r;
-    }
-    return 1;
-}
 
 __global__ void __launch_bounds__(JS_THREADS, 1) jacobi_small_kernel(const JacobiSmallParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -233,7 +277,8 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jacobi_small_kernel(const Jacob
                 int a, b;
                 if (grp == 0) { a = nm1; b = t; }
                 else { a = (t + grp) % nm1; b = (t - grp + nm1) % nm1; }
-                rotated |= rotate_pair_group(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld, ncols2, p.tol, gl);
+                rotated |= rotate_pair_cached<JS_GROUP, JS_NIT, false>(Xs + (size_t)a * ld, Xs + (size_t)b * ld, Js + (size_t)a * ld, Js + (size_t)b * ld,
+                                                                        ncols2, p.tol, gl);
             }
             __syncthreads();
         }
