@@ -108,15 +108,27 @@ def svd_small(M):
 
 
 def eigh_sym(N):
-    """Eigen-decomposition of a symmetric matrix, N = V diag(w) V^T (torch.linalg.eigh up to the order of the pairs): the left
-    singular vectors (K4 + K5) are orthonormal eigenvectors, the eigenvalues are their Rayleigh quotients (signed)."""
+    """Eigen-decomposition of a symmetric matrix, N = V diag(w) V^T (torch.linalg.eigh up to the order of the pairs).
+
+    The singular vectors of N are eigenvectors only where |lambda| is simple: a pair +lambda / -lambda (noise eigenvalues of either sign
+    on a norm matrix that is positive only up to truncation error) is ONE singular value, and an SVD may return any rotation of the two
+    eigenvectors -- Rayleigh quotients near 0 instead of +-lambda.  So the SVD is taken of N + sigma I with sigma = 1.01 ||N||_F >= the
+    spectral radius: every eigenvalue becomes positive, singular vectors = eigenvectors, and what is lost is relative accuracy of tiny
+    eigenvalues below eps * ||N|| -- which a symmetric eigensolver (LAPACK syevd behind torch.linalg.eigh) does not have either.
+    The eigenvalues are the Rayleigh quotients with the unshifted N (signed)."""
     N = N.contiguous()
-    # QR first: one-sided Jacobi on the triangular factor converges in ~6 sweeps instead of 13-18 on the symmetric matrix itself
-    Q, R = qr_small(N)
+    n = N.shape[0]
+    sigma = 1.01 * torch.linalg.matrix_norm(N)                   # device scalar, no host read
+    Ns = N + sigma * torch.eye(n, dtype=N.dtype, device=N.device)
+    # QR first: one-sided Jacobi on the triangular factor converges in a few sweeps
+    Q, R = qr_small(Ns)
     _, _, Jt, _ = ops.jacobi_svd(R)
-    V = ops.matmul(Q, Jt.t().contiguous())                   # left singular vectors of N = Q R = (Q Jt^T) S Wt
+    V = ops.matmul(Q, Jt.t().contiguous())                   # left singular vectors of N + sigma I = Q R = (Q Jt^T) S Wt
     w = (ops.matmul(N, V) * V).sum(dim=0)
-    return w, V
+    # ascending like torch.linalg.eigh: the callers' results are gauge invariant in exact arithmetic only -- gauge_fix inverts factors with
+    # condition numbers ~1e3, so the ORDER of the eigenpairs is visible at ~1e-9 in the updated tensors; keep the reference's order
+    w, order = torch.sort(w, stable=True)
+    return w, V[:, order].contiguous()
 
 
 def pinv_small(R, atol=1e-12):
