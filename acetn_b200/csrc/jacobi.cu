@@ -2,16 +2,13 @@
 // (reference: torch.linalg.svd of the projected matrix, acetn/linalg/fused_matmul_svd_lowrank.py:48, after the
 // tall factor has been reduced to a (chi+p) x (chi+p) core by K4 + one DGEMM).
 //
-// Rows of X are rotated pairwise until mutually orthogonal:  J X = diag(S) W.  One warp owns one row pair per
-// round-robin step (n/2 independent pairs per step, n-1 steps per sweep); the matrix (n <= ~1k, <= 8 MB with J)
-// stays L2 resident and the steps are separated by a cooperative grid barrier.  Rotations use the relative
-// criterion |x_p.x_q| <= tol ||x_p|| ||x_q||, which gives high relative accuracy of small singular values.
-#include <cooperative_groups.h>
+// Rows of X are rotated pairwise until mutually orthogonal:  J X = diag(S) W.  Rotations use the relative criterion
+// |x_p.x_q| <= tol ||x_p|| ||x_q||, which gives high relative accuracy of small singular values.  Two kernels:
+//   jacobi_small_kernel (q <= 112): the whole SVD on one CTA, X and J in its shared memory, one __syncthreads per step;
+//   jacobi_block_kernel (larger cores): row blocks of 8, every CTA of a cooperative grid stages a block pair from L2 per phase.
 #include <stdlib.h>
 
 #include "kernels.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace ab200 {
 
