@@ -15,6 +15,10 @@
 //     cond 1e20 (SURVEY.md section 7 hard part 2), where CholeskyQR would lose the trailing directions; such panels fail the pivot
 //     test and take this path, while well-conditioned panels (the first and last orthonormalisation of a projector, random benchmark
 //     tensors) take the short one.
+//
+// Two launch forms of the same algorithm: one kernel per stage (~25 launches per panel; any size), and -- for m <= 4096, q <= 130,
+// where those launches are pure latency -- ortho_fused_kernel: everything in ONE launch, one CTA per 256-row chunk, the stage
+// boundaries replaced by __syncthreads / a thread-block-cluster barrier / a cooperative grid barrier.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
