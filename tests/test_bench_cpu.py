@@ -47,3 +47,23 @@ def test_reference_arm_other_ranks_exit_quietly():
 def test_product_arm_needs_a_gpu():
     r = _run(["--D", "2", "--chi", "6", "--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_metric_and_config_name_the_measured_shape():
+    """BASELINE.json's metric string verbatim at the headline shape; other BASELINE configs (bench.py --D --chi) spell their shape out in
+    `metric` and in the L2 note, and both arms build the SAME `config` object (the driver compares them)."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    head = argparse.Namespace(D=8, chi=256, d=2)
+    assert bench.metric_name(head) == bench.METRIC
+    assert "D=8" in bench.METRIC and "chi=256" in bench.METRIC and str(base.get("unit", "sweeps/s")).split("/")[0][:5] in bench.METRIC + bench.UNIT
+    small = argparse.Namespace(D=4, chi=64, d=2)
+    assert "D=4 chi=64" in bench.metric_name(small)
+    c_head, c_small = bench.shared_config(head, 4, 4), bench.shared_config(small, 2, 2)
+    assert "exceed the 126 MB L2" in c_head["l2"] and "2.00 GiB" in c_head["l2"]
+    assert "launch-bound" in c_small["l2"] and c_small["cell"] == "2x2" and "D=4 chi=64" in c_small["workload"]
+    assert set(c_head) == set(c_small) == {"workload", "cell", "value_unit", "l2"}
