@@ -54,6 +54,10 @@ def test_workspace_queries_run_without_gpu(lib):
     rows, cols = _lib.i64_array([16384, 16384]), _lib.i64_array([16384, 16384])
     assert lib.acetn_b200_rsvd_workspace_bytes(2, rows, cols, 258) > 5 * 16384 * 258 * 8
     assert lib.acetn_b200_orthonormalize_workspace_bytes(16384, 258) > 0
+    # small matrices (m <= 4096, q <= 130) take the single-launch kernel: its coefficient / Gram partials come on top of the TSQR scratch
+    nchunks, nblk = 4, 3
+    assert lib.acetn_b200_orthonormalize_workspace_bytes(1024, 66) >= (nchunks * nblk + 2 * nchunks) * 32 * 33 * 8
+    assert lib.acetn_b200_orthonormalize_workspace_bytes(1024, 66) < lib.acetn_b200_orthonormalize_workspace_bytes(16384, 258)
     assert lib.acetn_b200_jacobi_svd_workspace_bytes(258) >= 2 * 258 * 258 * 8
     # the two-stage edge absorption: stage 1 holds P1t + T (2 GiB at D=8 chi=256), stage 2 only GEMM / normalisation scratch
     full = lib.acetn_b200_absorb_edge_workspace_bytes(256, 256, 256, 256, 8, 2)
