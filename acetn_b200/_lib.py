@@ -64,7 +64,7 @@ SIGNATURES = {
                                                    c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_fp64_peak_probe": (c_dbl, [c_vp, c_int, c_vp]),
     "acetn_b200_als_workspace_bytes": (c_sz, [c_i64] * 3),
-    "acetn_b200_als_solve": (c_int, [c_vp] * 5 + [c_i64] * 4 + [c_dbl, c_dbl, c_vp, c_vp, c_sz, c_vp]),
+    "acetn_b200_als_solve": (c_int, [c_vp] * 5 + [c_i64] * 4 + [c_dbl, c_dbl, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_site_rdm_workspace_bytes": (c_sz, [P_i64, c_i64, c_i64]),
     "acetn_b200_site_rdm": (c_int, [c_vp] * 9 + [P_i64, P_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "acetn_b200_bond_rdm_workspace_bytes": (c_sz, [P_i64, c_i64, c_i64]),

@@ -7,7 +7,10 @@
 //   a1r[y,u,p], a2r[x,u,q] (nD,bD,pD);  n12[y,x,Y,X] (nD^4);  n12g[Y,X,p,q];  a12g[y,x,p,q]
 //   S1[Y,U,p]   = sum n12g[Y,X,p,Q] a2r[X,U,Q]            R1[(Y,U),(y,u)] = sum n12[y,x,Y,X] a2r[x,u,q] a2r[X,U,q]
 //   S2[X,V,q]   = sum n12g[Y,X,P,q] a1r[Y,V,P]            R2[(X,V),(x,v)] = sum n12[y,x,Y,X] a1r[y,v,p] a1r[Y,V,p]
-//   R <- (R+R^T)/2 + eps*max|R|*I ;  R a = S by Cholesky ;  cost = <a12n|N|a12n> - 2 <a12n|N|a12g>
+//   method "cholesky": R <- (R+R^T)/2 + eps*max|R|*I ;  R a = S by Cholesky
+//   method "pinv" (als_solver.py:226-228 = als_solve.cpp:47-50): a = pinv((R+R^T)/2, hermitian, rcond = eps) S -- symmetric
+//     eigen-decomposition by a parallel two-sided Jacobi in the shared memory of CTA 0, eigenvalues below eps*max|w| dropped
+//   cost = <a12n|N|a12n> - 2 <a12n|N|a12g>
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
@@ -29,6 +32,8 @@ struct AlsParams {
     double* part;     // [grid][2] cost partials
     int* info;        // [0] iterations run, [1] cholesky failures
     int chol_in_smem;
+    int method;       // 0 = cholesky, 1 = pinv
+    double* V;        // n x n eigenvectors (pinv; global, L2 resident)
 };
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* red) {
@@ -50,6 +55,100 @@ __device__ __forceinline__ double block_reduce_max(double v, double* red) {
     double s = 0.0;
     for (int i = 0; i < ALS_THREADS / 32; i++) s = fmax(s, red[i]);
     return s;
+}
+
+// a = pinv(M, hermitian, rcond) S for the symmetric n x n matrix M (shared memory, pitch ldm), CTA-wide.  Parallel two-sided Jacobi:
+// the n/2 disjoint pairs of a round-robin step get their rotation from (m_pp, m_qq, m_pq); row phase M <- J^T M, column phase
+// M <- M J and V <- V J; a sweep that rotates nothing ends the iteration.  Absolute accuracy eps*||M|| like a LAPACK symmetric
+// eigensolver.  S (n x pD, global) is overwritten with the solution.  rot: shared scratch [n] (cos, sin per pair).
+__device__ void als_pinv_solve(double* M, int ldm, int n, double* V, double* S, int pD, double rcond, double* rot, double* red) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int np = n + (n & 1);                      // an odd n gets a bye
+    const int npairs = np / 2, nm1 = np - 1;
+    for (int o = tid; o < n * n; o += T) V[o] = (o / n == o % n) ? 1.0 : 0.0;
+    double fro = 0.0;
+    for (int o = tid; o < n * n; o += T) { const double v = M[(o / n) * ldm + (o % n)]; fro += v * v; }
+    fro = sqrt(block_reduce_sum(fro, red));
+    const double small = 1e-17 * fro;                // couplings below eps*||M|| are zero to working accuracy
+    __shared__ int s_rotated;
+    for (int sweep = 0; sweep < 40; sweep++) {
+        if (tid == 0) s_rotated = 0;
+        __syncthreads();
+        for (int t = 0; t < nm1; t++) {
+            for (int k = tid; k < npairs; k += T) {
+                int a, b;
+                if (k == 0) { a = nm1; b = t; }
+                else { a = (t + k) % nm1; b = (t - k + nm1) % nm1; }
+                double c = 1.0, sn = 0.0;
+                if (a < n && b < n) {
+                    const double mpq = M[a * ldm + b];
+                    if (fabs(mpq) > small) {
+                        const double tau = (M[b * ldm + b] - M[a * ldm + a]) / (2.0 * mpq);
+                        const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = rsqrt(1.0 + tt * tt);
+                        sn = c * tt;
+                        s_rotated = 1;
+                    }
+                }
+                rot[2 * k] = c; rot[2 * k + 1] = sn;
+            }
+            __syncthreads();
+            // rows:  M[a,:] <- c M[a,:] - s M[b,:] ;  M[b,:] <- s M[a,:] + c M[b,:]
+            for (int o = tid; o < npairs * n; o += T) {
+                const int k = o / n, col = o - k * n;
+                int a, b;
+                if (k == 0) { a = nm1; b = t; }
+                else { a = (t + k) % nm1; b = (t - k + nm1) % nm1; }
+                const double c = rot[2 * k], sn = rot[2 * k + 1];
+                if (a < n && b < n && sn != 0.0) {
+                    const double x = M[a * ldm + col], y = M[b * ldm + col];
+                    M[a * ldm + col] = c * x - sn * y;
+                    M[b * ldm + col] = sn * x + c * y;
+                }
+            }
+            __syncthreads();
+            // columns of M and of V
+            for (int o = tid; o < npairs * n; o += T) {
+                const int k = o / n, row = o - k * n;
+                int a, b;
+                if (k == 0) { a = nm1; b = t; }
+                else { a = (t + k) % nm1; b = (t - k + nm1) % nm1; }
+                const double c = rot[2 * k], sn = rot[2 * k + 1];
+                if (a < n && b < n && sn != 0.0) {
+                    const double x = M[row * ldm + a], y = M[row * ldm + b];
+                    M[row * ldm + a] = c * x - sn * y;
+                    M[row * ldm + b] = sn * x + c * y;
+                    const double vx = V[row * n + a], vy = V[row * n + b];
+                    V[row * n + a] = c * vx - sn * vy;
+                    V[row * n + b] = sn * vx + c * vy;
+                }
+            }
+            __syncthreads();
+        }
+        if (s_rotated == 0) break;
+        __syncthreads();
+    }
+    // a = V diag(1/w, |w| > rcond max|w|) V^T S
+    double wmax = 0.0;
+    for (int i = tid; i < n; i += T) wmax = fmax(wmax, fabs(M[i * ldm + i]));
+    wmax = block_reduce_max(wmax, red);
+    // y = diag(1/w, kept) V^T S
+    for (int o = tid; o < n * pD; o += T) {
+        const int i = o / pD, ph = o - i * pD;
+        const double w = M[i * ldm + i];
+        double acc = 0.0;
+        for (int r = 0; r < n; r++) acc += V[r * n + i] * S[r * pD + ph];
+        // the diagonal entry is read by the other pD-1 threads of this row: the result is staged next to V, not in M
+        V[n * n + o] = (fabs(w) > rcond * wmax) ? acc / w : 0.0;
+    }
+    __syncthreads();
+    for (int o = tid; o < n * pD; o += T) {
+        const int r = o / pD, ph = o - r * pD;
+        double acc = 0.0;
+        for (int i = 0; i < n; i++) acc += V[r * n + i] * V[n * n + i * pD + ph];
+        S[o] = acc;
+    }
+    __syncthreads();
 }
 
 // which = 0: solve for a1r with a2r fixed ; which = 1: solve for a2r with a1r fixed
@@ -99,6 +198,7 @@ __device__ void als_half_step(const AlsParams& p, int which, cg::grid_group& gri
     if (blockIdx.x == 0) {
         const int tid = threadIdx.x, T = blockDim.x;
         const int ldm = n + 1;
+        __shared__ double smem_rot[2 * 260];            // (cos, sin) per pair of a Jacobi step, n <= 512
         double* M = p.chol_in_smem ? smem : p.G;        // G is free now; (n x ldm needs n*(n+1) <= allocated (n+1)^2)
         double mx = 0.0;
         for (int o = tid; o < n * n; o += T) {
@@ -108,6 +208,12 @@ __device__ void als_half_step(const AlsParams& p, int which, cg::grid_group& gri
             mx = fmax(mx, fabs(v));
         }
         mx = block_reduce_max(mx, red);
+        if (p.method == 1) {
+            __syncthreads();
+            als_pinv_solve(M, ldm, n, p.V, p.S, pD, p.epsilon, smem_rot, red);
+            double* dstp = which == 0 ? p.a1r : p.a2r;
+            for (int o = tid; o < n * pD; o += T) dstp[o] = p.S[o];
+        } else {
         for (int i = tid; i < n; i += T) M[i * ldm + i] += p.epsilon * mx;
         __syncthreads();
         for (int j = 0; j < n; j++) {
@@ -148,6 +254,7 @@ __device__ void als_half_step(const AlsParams& p, int which, cg::grid_group& gri
         }
         double* dst = which == 0 ? p.a1r : p.a2r;
         for (int o = tid; o < n * pD; o += T) dst[o] = p.S[o];
+        }
     }
     grid.sync();
 }
@@ -207,12 +314,15 @@ __global__ void __launch_bounds__(ALS_THREADS, 1) als_kernel(AlsParams p) {
 
 size_t als_workspace_bytes(int nD, int bD, int pD) {
     size_t n = (size_t)nD * bD;
-    return ws_round((n + 1) * (n + 1) * 8) + ws_round(n * n * 8) + ws_round(n * pD * 8) + ws_round(148 * 2 * 8) + 1024;
+    return ws_round((n + 1) * (n + 1) * 8) + ws_round(n * n * 8) + ws_round(n * pD * 8) + ws_round(148 * 2 * 8) +
+           ws_round((n * n + n * pD) * 8) + 1024;          // + eigenvectors and the scaled V^T S of the pinv method
 }
 
 int als_solve_launch(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int nD, int bD, int pD,
-                     int niter, double tol, double epsilon, int* info, void* wsp, size_t ws_bytes, cudaStream_t s) {
+                     int niter, double tol, double epsilon, int method, int* info, void* wsp, size_t ws_bytes, cudaStream_t s) {
     AB_REQUIRE(nD >= 1 && bD >= 1 && pD >= 1 && pD <= 16, "als_solve: bad dims nD=%d bD=%d pD=%d", nD, bD, pD);
+    AB_REQUIRE(method == 0 || method == 1, "als_solve: method must be 0 (cholesky) or 1 (pinv), got %d", method);
+    AB_REQUIRE(method == 0 || nD * bD <= 512, "als_solve: pinv method supports nD*bD <= 512 (got %d)", nD * bD);
     const size_t n = (size_t)nD * bD;
     Workspace ws(wsp, ws_bytes);
     AlsParams p;
@@ -222,9 +332,12 @@ int als_solve_launch(double* a1r, double* a2r, const double* n12g, const double*
     p.R = ws.take<double>(n * n);
     p.S = ws.take<double>(n * pD);
     p.part = ws.take<double>(148 * 2);
+    p.V = ws.take<double>(n * n + n * pD);
+    p.method = method;
     if (ws.overflow) { set_error("als_solve: workspace too small"); return ERR_WORKSPACE; }
     size_t chol_bytes = n * (n + 1) * 8, cost_bytes = (size_t)nD * nD * pD * pD * 8;
     p.chol_in_smem = chol_bytes <= 200 * 1024 ? 1 : 0;
+    AB_REQUIRE(method == 0 || p.chol_in_smem, "als_solve: pinv method needs the normal matrix in shared memory (nD*bD <= 159)");
     size_t smem = p.chol_in_smem ? (chol_bytes > cost_bytes ? chol_bytes : cost_bytes) : cost_bytes;
     AB_REQUIRE(smem <= 220 * 1024, "als_solve: nD^2 pD^2 too large for shared memory");
     AB_ENSURE_SMEM(als_kernel, smem);

@@ -15,7 +15,7 @@ void reset_launch_count();
 double dmma_peak_launch(double* scratch, int iters, cudaStream_t s);
 size_t als_workspace_bytes(int nD, int bD, int pD);
 int als_solve_launch(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int nD, int bD, int pD,
-                     int niter, double tol, double epsilon, int* info, void* wsp, size_t ws_bytes, cudaStream_t s);
+                     int niter, double tol, double epsilon, int method, int* info, void* wsp, size_t ws_bytes, cudaStream_t s);
 int double_layer_fused_supported(int64_t D, int64_t d);
 int double_layer_fused_colexp_supported(int64_t D, int64_t d);
 int double_layer_fused_launch(const double* X, int64_t n0, int64_t n1, int64_t in_s0, int64_t in_s1, const int64_t* in_es,
@@ -625,9 +625,10 @@ double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream) { retu
 
 size_t acetn_b200_als_workspace_bytes(int64_t nD, int64_t bD, int64_t pD) { return als_workspace_bytes((int)nD, (int)bD, (int)pD); }
 int acetn_b200_als_solve(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int64_t nD, int64_t bD,
-                         int64_t pD, int64_t niter, double tol, double epsilon, int32_t* info, void* ws, size_t ws_bytes, void* stream) {
-    return als_solve_launch(a1r, a2r, n12g, n12, a12g, (int)nD, (int)bD, (int)pD, (int)niter, tol, epsilon, (int*)info, ws, ws_bytes,
-                            S_(stream));
+                         int64_t pD, int64_t niter, double tol, double epsilon, int64_t method, int32_t* info, void* ws, size_t ws_bytes,
+                         void* stream) {
+    return als_solve_launch(a1r, a2r, n12g, n12, a12g, (int)nD, (int)bD, (int)pD, (int)niter, tol, epsilon, (int)method, (int*)info, ws,
+                            ws_bytes, S_(stream));
 }
 
 int acetn_b200_permute(double* dst, const double* src, int nd, const int64_t* dims, const int64_t* strides, void* stream) {

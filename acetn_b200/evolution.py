@@ -23,10 +23,12 @@ def build_norm_tensor(ipeps, bond, a1q, a2q):
 
 
 class ALSSolver:
-    """als_solver.py:6-82.  method "cholesky" (default): the whole iteration loop in libacetn_b200.so (K6, one cooperative
-    kernel, convergence test on the device).  method "pinv" (als_solver.py:226-228 = csrc/evolution/als_solve.cpp:47-50): the
-    reference's host-driven loop, every contraction / decomposition on the library's kernels (K1 contractions, K4 + K5
-    symmetric eigen-decomposition), one host read of the cost per iteration like the reference (als_solver.py:78-79)."""
+    """als_solver.py:6-82.  Both methods run the whole iteration loop in libacetn_b200.so (K6, one cooperative kernel, convergence
+    test on the device): "cholesky" (default) and "pinv" (als_solver.py:226-228 = csrc/evolution/als_solve.cpp:47-50; symmetric
+    eigen-decomposition by two-sided Jacobi inside the kernel).  Normal matrices too large for the kernel's shared memory
+    (nD * bD > PINV_KERNEL_MAX, i.e. D >= 9 at d = 2) take the reference's host-driven pinv loop on the library's kernels (K1
+    contractions, K4 + K5 eigen-decomposition, one host read of the cost per iteration like the reference, als_solver.py:78-79)."""
+    PINV_KERNEL_MAX = 159
 
     def __init__(self, n12, a12g, ar_shape, config):
         self.niter = config.als_niter
@@ -52,9 +54,11 @@ class ALSSolver:
 
     def solve(self):
         a1r, a2r, n12g = self.initialize_tensors()
-        if self.method == "pinv":
+        nD, bD, _ = self.ar_shape
+        if self.method == "pinv" and nD * bD > self.PINV_KERNEL_MAX:
             return self.solve_pinv(a1r, a2r, n12g)
-        a1r, a2r, self.info = ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon)
+        a1r, a2r, self.info = ops.als_solve(a1r, a2r, n12g, self.n12, self.a12g, niter=self.niter, tol=self.tol, epsilon=self.epsilon,
+                                            method=self.method)
         return a1r, a2r
 
     # ---- method "pinv" ------------------------------------------------------------------------------------------------

@@ -543,9 +543,14 @@ def frob_normalize(x):
     return x
 
 
-def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
-    """als_solver.py:55-82 / csrc/evolution/als_solve.cpp:107-137 (cholesky method).  Returns (a1r, a2r, info) with
-    info = device int32[2] {iterations run, non-positive Cholesky pivots}."""
+ALS_METHODS = {"cholesky": 0, "pinv": 1}
+
+
+def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12, method="cholesky"):
+    """als_solver.py:55-82 / csrc/evolution/als_solve.cpp:107-137, method "cholesky" or "pinv" (als_solver.py:218-229).  Returns
+    (a1r, a2r, info) with info = device int32[2] {iterations run, non-positive Cholesky pivots}."""
+    if method not in ALS_METHODS:
+        raise ValueError(f"Invalid als_method: {method} provided.")
     dev = _require_cuda(a1r, a2r, n12g, n12, a12g)
     a1 = a1r.contiguous().clone()
     a2 = a2r.contiguous().clone()
@@ -556,7 +561,7 @@ def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
     ws = _ws(dev, lib.acetn_b200_als_workspace_bytes(nD, bD, pD))
     with _on(dev):
         st = lib.acetn_b200_als_solve(_p(a1), _p(a2), _p(n12g), _p(n12), _p(a12g), nD, bD, pD, int(niter), float(tol), float(epsilon),
-                                      _p(info), _p(ws), ws.numel(), _stream(dev))
+                                      ALS_METHODS[method], _p(info), _p(ws), ws.numel(), _stream(dev))
     _lib.check(st, "als_solve")
     return a1, a2, info
 

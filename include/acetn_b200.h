@@ -204,15 +204,18 @@ int acetn_b200_projectors_from_usv_enc(const double* Q1, const void* enc1, int64
 double acetn_b200_fp64_peak_probe(void* scratch, int iters, void* stream);
 
 /* ---- ALS inner solver of the full update: ALSSolver.solve_torch (acetn/evolution/als_solver.py:55-82) = als_solve
- *      of the reference's cuTENSOR extension (csrc/evolution/als_solve.cpp:107-137), cholesky method.
+ *      of the reference's cuTENSOR extension (csrc/evolution/als_solve.cpp:107-137).
+ *   method 0 = "cholesky" (als_solver.py:218-225, als_solve.cpp:25-46): (R + R^T)/2 + epsilon max|R| I solved by Cholesky;
+ *   method 1 = "pinv" (als_solver.py:226-228, als_solve.cpp:47-50): pinv((R + R^T)/2, hermitian, rcond = epsilon) S, the symmetric
+ *   eigen-decomposition by two-sided Jacobi inside the kernel (needs nD*bD <= 159).
  *   a1r, a2r (nD,bD,pD): in = initial guess (als_solver.py:117-146), out = result.  n12 (nD^4) [y,x,Y,X],
  *   n12g (nD,nD,pD,pD) [Y,X,p,q], a12g (nD,nD,pD,pD) [y,x,p,q].  The whole loop (<= niter iterations, stop when the
  *   relative cost change < tol and i > 1) runs in one cooperative kernel; info (device int32[2]) = {iterations run,
  *   number of non-positive Cholesky pivots met (0 = clean)}. */
 size_t acetn_b200_als_workspace_bytes(int64_t nD, int64_t bD, int64_t pD);
 int acetn_b200_als_solve(double* a1r, double* a2r, const double* n12g, const double* n12, const double* a12g, int64_t nD,
-                         int64_t bD, int64_t pD, int64_t niter, double tol, double epsilon, int32_t* info, void* ws,
-                         size_t ws_bytes, void* stream);
+                         int64_t bD, int64_t pD, int64_t niter, double tol, double epsilon, int64_t method, int32_t* info,
+                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---- environment contractions of `measure` and of the full update (SURVEY.md 8b minimum set; acetn_b200/csrc/environment.cu) --------
  *   Every step is a K1 launch whose index descriptors absorb the leg permutations of the reference's einsum chain.

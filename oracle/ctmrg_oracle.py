@@ -561,19 +561,21 @@ def als_cost(a1r, a2r, a12g, n12):
     return d2.real - 2 * d3.real
 
 
-def _als_solve_ar(R, S, epsilon):
-    """als_solver.py:197-229 (cholesky branch)."""
+def _als_solve_ar(R, S, epsilon, method="cholesky"):
+    """als_solver.py:197-229: cholesky branch (:218-225) or pinv branch (:226-228)."""
     nD, bD, pD = S.shape
     S = S.reshape(nD * bD, pD)
     R = R.reshape(nD * bD, nD * bD)
     R = 0.5 * (R + R.mH)
+    if method == "pinv":
+        return (torch.linalg.pinv(R, hermitian=True, rcond=epsilon) @ S).reshape(nD, bD, pD)
     R = R + epsilon * R.abs().max() * torch.eye(R.shape[0], dtype=R.dtype, device=R.device)
     L = torch.linalg.cholesky(R)
     Y = torch.linalg.solve_triangular(L, S, upper=False)
     return torch.linalg.solve_triangular(L.mH, Y, upper=True).reshape(nD, bD, pD)
 
 
-def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
+def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12, method="cholesky"):
     """als_solver.py:55-82 (solve_torch) = csrc/evolution/als_solve.cpp:55-105.  Returns (a1r, a2r, iterations run)."""
     d1 = als_cost(a1r, a2r, a12g, n12).abs()
     it = 0
@@ -582,11 +584,11 @@ def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
         S = torch.einsum("YXpQ,XUQ->YUp", n12g, a2r.conj())
         R = torch.einsum("yxYX,xuq->yYXuq", n12, a2r)
         R = torch.einsum("yYXuQ,XUQ->YUyu", R, a2r.conj())
-        a1r = _als_solve_ar(R, S, epsilon)
+        a1r = _als_solve_ar(R, S, epsilon, method)
         S = torch.einsum("YXPq,YVP->XVq", n12g, a1r.conj())
         R = torch.einsum("yxYX,yvp->xYXvp", n12, a1r)
         R = torch.einsum("xYXvP,YVP->XVxv", R, a1r.conj())
-        a2r = _als_solve_ar(R, S, epsilon)
+        a2r = _als_solve_ar(R, S, epsilon, method)
         d2 = als_cost(a1r, a2r, a12g, n12)
         error = abs(d2 - d1) / d1.abs()
         if error < tol and i > 1:

@@ -183,8 +183,8 @@ def frob_normalize(x):
     return x
 
 
-def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12):
-    a1, a2, it = orc.als_solve(a1r.clone(), a2r.clone(), n12g, n12, a12g, niter=niter, tol=tol, epsilon=epsilon)
+def als_solve(a1r, a2r, n12g, n12, a12g, niter=100, tol=1e-15, epsilon=1e-12, method="cholesky"):
+    a1, a2, it = orc.als_solve(a1r.clone(), a2r.clone(), n12g, n12, a12g, niter=niter, tol=tol, epsilon=epsilon, method=method)
     return a1.contiguous(), a2.contiguous(), torch.tensor([it, 0], dtype=torch.int32)
 
 
