@@ -2,6 +2,7 @@
 strides and the current CUDA stream.  No torch types cross the boundary."""
 import contextlib
 import ctypes
+import math
 
 import torch
 
@@ -438,7 +439,7 @@ def contract(spec, A, B):
     N = "".join(c for c in out if c in sb and c not in sa)
     if set(batch + M + N) != set(out) or set(batch + M + K) != set(sa) or set(batch + K + N) != set(sb):
         raise ValueError(f"contract: unsupported spec {spec} (traces / outer sums are not handled)")
-    prod = lambda s: int(torch.tensor([ext[c] for c in s]).prod()) if s else 1   # noqa: E731
+    prod = lambda s: math.prod(ext[c] for c in s)   # noqa: E731
     nb, m, n, k = prod(batch), prod(M), prod(N), prod(K)
     Av, ta = _as_layout(A, sa, (batch, M), K)        # [b, M, K] ("fs") or [b, K, M] ("sf")
     Bv, tb = _as_layout(B, sb, (batch, K), N)        # [b, K, N] ("fs") or [b, N, K] ("sf")
